@@ -1,0 +1,287 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the 6DOF environment step on B200 (BASELINE.json metric), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # ours (CUDA path through the C ABI)
+    python bench.py --impl reference [--steps K] [--warmup W]      # the reference's Python/scipy CPU path (oracle port)
+
+A "step" is one pass of the hot path over one batch: ONE rlr_step launch advancing every environment of the rank by
+one agent step (action mapping -> adaptive RK45 solve with ground event -> reward -> TimeLimit -> auto-reset).
+N = 1 runs BASELINE config 3 (6DOF `env_config`, 65 536 envs); N > 1 keeps 65 536 envs per GPU (weak scaling; envs are
+keyed by their global index, no data-path collective) and adds the per-rollout NCCL all-gather of the episode statistics
+to the timed region.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 65536
+PREP_STEPS = 150            # untimed state preparation: desynchronise episodes so resets/events occur at their steady rate
+FLOP_STEP, FLOP_ATTEMPT = 540, 1530      # algorithmic fp64 flop per 6DOF env step: 540 + 1530*k
+BYTES_STEP = 320                          # algorithmic HBM bytes per env step when state round-trips
+
+
+def env_config():
+    from tests import goldutil as G
+    return G.cfg6()
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path (Python + scipy.solve_ivp), as restated in oracle/scipy_port.py
+    (bit-identical to the live reference on the golden vectors), on every host core.  One bench "step" = a bounded sample:
+    each of the P worker processes advances its environment for `--ref-seconds` of wall time."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import scipy_port as SP
+    cores = os.cpu_count()
+    vals = []
+    farm = SP.CpuFarm(6, env_config(), 800, procs=cores)
+    for i in range(args.warmup + args.steps):
+        r = farm.sample(args.ref_seconds)
+        if i >= args.warmup:
+            vals.append(r)
+    farm.close()
+    steps = sum(v["steps"] for v in vals)
+    wall = sum(v["wall_s"] for v in vals)
+    value = steps / wall
+    sample = f"{cores} single-env worker processes x {args.ref_seconds:.1f} s of random-action 6DOF env_config steps per bench step"
+    line = {"impl": "reference", "metric": "env_steps_per_sec_6dof", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "6DOF env_config (configuration_file.py:4-34), random U(-1,1) f32 actions, TimeLimit 800, auto-reset",
+                       "envs": cores},
+            "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from rl_rocket_b200.config import EnvSpec
+    from rl_rocket_b200.engine import RocketBatch, fma_peak
+    from rl_rocket_b200.vec_env import RocketVecEnv
+
+    n = args.envs_per_gpu
+    K, W = args.steps, args.warmup
+    cfg = env_config()
+    spec = EnvSpec(6, max_episode_steps=800, **cfg)
+    env = RocketBatch(spec, n, device=dev, seed=42, env_offset=rank * n, math_mode=args.math)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    env.reset()
+    chunk = torch.empty((PREP_STEPS, n, 3), device=dev)
+    chunk.uniform_(-1, 1, generator=gen)
+    for t in range(PREP_STEPS):
+        env.step_tensor(chunk[t])
+    actions = torch.empty((W + K, n, 3), device=dev)
+    actions.uniform_(-1, 1, generator=gen)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if args.l2_flush else None
+    stat_gather = torch.zeros((world, 8), dtype=torch.int64, device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for t in range(W):
+        env.step_tensor(actions[t])
+    env.read_stats(reset=True)
+    launches0 = env.launches
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K + 1)]
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    barrier()
+    t_wall0 = time.perf_counter()
+    for t in range(K):
+        if flush is not None:
+            flush.zero_()                    # evict L2 between timed iterations (outside the event pair)
+        ev[t][0].record()
+        env.step_tensor(actions[W + t])
+        ev[t][1].record()
+    # per-rollout exchange of returns / done counts (NCCL all-gather of the 8-slot statistics record), timed
+    ev[K][0].record()
+    if world > 1:
+        dist.all_gather_into_tensor(stat_gather, env.stats.unsqueeze(0))
+    ev[K][1].record()
+    barrier()
+    wall_ms = (time.perf_counter() - t_wall0) * 1e3
+    step_ms = [a.elapsed_time(b) for a, b in ev[:K]]
+    gather_ms = ev[K][0].elapsed_time(ev[K][1]) if world > 1 else 0.0
+    dev_ms = sum(step_ms) + gather_ms
+    clocks = sampler.stop() if rank == 0 else None
+    launches = env.launches - launches0
+    t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    max_ms = float(t_ms.item())
+    st = env.read_stats()
+    if world > 1:
+        tot = stat_gather.sum(0).cpu().tolist()
+        st_all = {"steps": tot[0], "attempts": tot[1], "done": tot[2]}
+    else:
+        st_all = st
+    value = n * world * K / (max_ms * 1e-3)
+
+    line = None
+    if rank == 0:
+        # ---- back-to-back (no flush) and fused-rollout variants, device-timed, for the record
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for t in range(K):
+            env.step_tensor(actions[W + t])
+        e1.record()
+        e1.synchronize()
+        b2b = n * K / (e0.elapsed_time(e1) * 1e-3)
+        Tr = min(K, 200)
+        e0.record()
+        env.rollout(actions[W:W + Tr])
+        e1.record()
+        e1.synchronize()
+        fused = n * Tr / (e0.elapsed_time(e1) * 1e-3)
+        # ---- roofline of the dominant kernel (step_kernel<Sys6>): FP64 ALU bound, peak measured in this run
+        peak = fma_peak("f64", device=dev)
+        flops = FLOP_STEP * st["steps"] + FLOP_ATTEMPT * st["attempts"]
+        kern_s = sum(step_ms) * 1e-3
+        achieved = flops / kern_s / 1e12
+        hbm_gbs = BYTES_STEP * st["steps"] / kern_s / 1e9
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:  # noqa: BLE001
+            hbm_peak = 6650.0
+        roofline = {"bound": "fp64_alu", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "traffic": None, "kernel": "step_kernel<Sys6>", "peak_source": "rlr_fma_peak DFMA microbench in this run "
+                    "(MEASURED_PEAKS.json has no FP64 figure)", "flop_model": "540 + 1530*attempts per env step; attempts counted by the kernel",
+                    "attempts_per_step": st["attempts"] / max(1, st["steps"]),
+                    "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak, "bytes_per_env_step": BYTES_STEP}}
+        # ---- end to end through the public VecEnv API with HOST buffers (pinned), H2D + D2H inside the timed region
+        venv = RocketVecEnv(n, dof=6, max_episode_steps=800, device=dev, math_mode=args.math, **cfg)
+        venv.reset_tensor()
+        for t in range(PREP_STEPS):
+            venv.step_tensor(chunk[t])
+        Ke = min(K, 200)
+        h_actions = [actions[W + t].cpu().pin_memory() for t in range(Ke)]
+        for t in range(3):
+            venv.step_host(h_actions[t])
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for t in range(Ke):
+            venv.step_host(h_actions[t])
+        torch.cuda.synchronize(dev)
+        e2e = n * Ke / (time.perf_counter() - t0)
+        e2e_d = {"value": e2e * world, "unit": "env-steps/s", "h2d_bytes_per_step": venv.h2d_bytes_per_step(),
+                 "d2h_bytes_per_step": venv.d2h_bytes_per_step(), "note": "RocketVecEnv.step_host: pinned host actions in, obs/reward/done "
+                 "out; measured on rank 0 and scaled by the rank count (ranks are independent)"}
+        # ---- CPU baseline: the reference's Python/scipy path (oracle port) on this box's host cores, bounded sample
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import scipy_port as SP
+            r = SP.cpu_throughput(6, cfg, 800, seconds=args.cpu_seconds, warm=1.0)
+            cpu = {"value": r["value"], "unit": "env-steps/s", "cores": r["cores"], "kind": "port",
+                   "sample": f"{r['cores']} single-env processes x {args.cpu_seconds:.0f} s, random actions, auto-reset ({r['steps']} steps)"}
+        line = {"metric": "env_steps_per_sec_6dof", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": "BASELINE config 3: 6DOF env_config (configuration_file.py:4-34), %d envs per GPU, random U(-1,1) "
+                           "f32 actions, TimeLimit 800, auto-reset, one rlr_step launch per step" % n, "envs_per_gpu": n,
+                           "total_envs": n * world, "math_mode": args.math,
+                           "l2": "256 MiB flush between timed steps" if args.l2_flush else "no flush",
+                           "state_prep": f"{PREP_STEPS} untimed random-action steps so episodes are desynchronised",
+                           "collective": "all_gather of the 64-byte episode-statistics record per rank (NCCL), timed" if world > 1 else None},
+                "clocks": clocks, "e2e": e2e_d, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                "episodes_finished": st_all["done"], "wall_ms_timed_region": wall_ms,
+                "variants": {"back_to_back_no_flush": b2b, "fused_rollout_kernel": fused, "unit": "env-steps/s (rank 0 only)"}}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--math", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--no-l2-flush", dest="l2_flush", action="store_false")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--ref-seconds", type=float, default=2.0)
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        if args.steps > 20:
+            args.steps = 20        # bounded: every reference "step" is args.ref_seconds of CPU work on all cores
+        run_reference(args)
+    else:
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        if world == 1 and args.gpus > 1:
+            # convenience: re-launch under torchrun, one rank per GPU
+            cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+                   "--master-port", "29511"] + sys.argv
+            sys.exit(subprocess.call(cmd))
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

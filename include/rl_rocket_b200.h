@@ -1,0 +1,148 @@
+/*
+ * rl_rocket_b200.h -- C ABI of the B200-native batched RL_rocket environment step.
+ *
+ * One shared library (rl_rocket_b200/_C/librlrocket.so, built by nvcc for sm_100a) exports the
+ * entry points below.  They are what a binding of the reference's environment layer would call
+ * instead of its Python/scipy path; INTEGRATION.md shows the ctypes stub.
+ *
+ * Reference interfaces replaced (paths relative to Tuxliri/RL_rocket):
+ *   rlr_reset      Rocket6DOF.reset  my_environment/envs/rocket_env.py:665-688   (+ Simulator6DOF.__init__ utils/simulator.py:180-225)
+ *                  Rocket.reset      my_environment/envs/rocket_env.py:137-148   (+ Simulator3DOF.__init__ utils/simulator.py:13-53)
+ *   rlr_step       Rocket6DOF.step   my_environment/envs/rocket_env.py:690-719   -> Simulator6DOF.step utils/simulator.py:227-257
+ *                  Rocket.step       my_environment/envs/rocket_env.py:150-175   -> Simulator3DOF.step utils/simulator.py:55-86
+ *                  + gym TimeLimit.step / SB3 DummyVecEnv.step_wait semantics (main_6DOF.py:21-22,71; main.py:65-70,105)
+ *                  + wrappers DiscreteActions3DOF / RewardAnnealing (my_environment/wrappers/wrappers.py:24-35,68-86)
+ *   rlr_rollout    T consecutive rlr_step calls fused in one launch (state stays in registers)
+ *   rlr_stats_*    the per-episode bookkeeping SB3's Monitor does on the host (main.py:65-70)
+ *
+ * Conventions
+ *   - Every function returns 0 on success or a negative RLR_E_* code; rlr_last_error() gives a
+ *     thread-local message.  Numerical failure of the integrator is NOT an error: as in the
+ *     reference (rocket_env.py:702, bool(status)) it terminates the episode.
+ *   - All pointers are DEVICE pointers into caller-owned memory (PyTorch tensors' data_ptr());
+ *     the library never allocates, frees or synchronises.  Work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream).
+ *   - State is structure-of-arrays: y[c * n + i] for component c of environment i, n = number of
+ *     environments in this call.  Observations / actions are row-major [n][dim] as SB3 expects.
+ */
+#ifndef RL_ROCKET_B200_H
+#define RL_ROCKET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLR_ABI_VERSION 1
+#define RLR_NMAX 14          /* state components: 14 (6DOF), 7 (3DOF / 1DOF) */
+#define RLR_MAX_DISCRETE 16
+
+enum { RLR_OK = 0, RLR_E_INVALID = -1, RLR_E_CUDA = -2, RLR_E_UNSUPPORTED = -3 };
+
+/* action_kind */
+enum {
+    RLR_ACT_NORMALIZED = 0,  /* f32 [n][3|2|1] in [-1,1]; mapped as _denormalize_action (rocket_env.py:969-981 / :395-406) */
+    RLR_ACT_PHYSICAL   = 1,  /* f32 [n][3|2]  already de-normalised (gimbal [rad] ..., thrust [N]) */
+    RLR_ACT_DISCRETE   = 2   /* i64 [n] index into RlrParams.discrete_table (DiscreteActions3DOF, wrappers.py:24-35) */
+};
+
+/* math_mode */
+enum {
+    RLR_MATH_EXACT = 0,      /* IEEE op-for-op sequence of the reference (no FMA contraction, true divisions) */
+    RLR_MATH_FAST  = 1       /* FMA contraction + reciprocal multiplies; deviation bounded in tests (<= 1e-9 normalised) */
+};
+
+/* precision of the integrated state */
+enum { RLR_F64 = 0, RLR_F32 = 1 };
+
+/* Host-side POD, copied by value into kernel parameters (< 1 KB). Filled by rl_rocket_b200/config.py. */
+typedef struct RlrParams {
+    int32_t dof;                 /* 6, 3 or 1 (1DOF toy problem of README.md:4-8: 3DOF with gimbal 0, obs (z, vz)) */
+    int32_t reward_mode;         /* 0 shaped reward; 1 RewardAnnealing */
+    int32_t max_episode_steps;   /* TimeLimit; <= 0 disables */
+    int32_t dt_ms;               /* timestep in whole milliseconds: t_k = k*dt_ms/1000 (simulator.py:245 rounds t to 3 decimals) */
+    double  dt;
+    double  normalizer[RLR_NMAX];
+    float   ic_low[RLR_NMAX], ic_high[RLR_NMAX];   /* init_space Box (rocket_env.py:564-567 / :57-60) */
+    float   pos_low[3], pos_high[3];               /* 6DOF position_bounds_space (rocket_env.py:615-620) */
+    double  x_left, x_right, y_up;                 /* 3DOF bounds (rocket_env.py:97-100) */
+    double  alfa, beta, eta, gamma, delta, kappa, xi;
+    double  waypoint, landing_radius, maximum_velocity;
+    double  att_traj_limit[3], att_land_limit[3], omega_lim[3];
+    double  max_gimbal;
+    float   max_thrust;
+    int32_t n_discrete;
+    float   discrete_table[2 * RLR_MAX_DISCRETE];  /* physical (gimbal, thrust) pairs */
+} RlrParams;
+
+/* Persistent per-environment state (device pointers, caller-owned). */
+typedef struct RlrState {
+    void*    y;          /* f64 (RLR_F64) or f32 (RLR_F32) [ndim][n] */
+    int32_t* k;          /* [n] steps taken in the current episode */
+    int32_t* episode;    /* [n] episode counter (keys the reset RNG) */
+    float*   v0;         /* [n] |v| of the episode's initial condition (vtarg, rocket_env.py:989-991) */
+    double*  ep_ret;     /* [n] running undiscounted return */
+} RlrState;
+
+/* Per-call outputs; any pointer may be NULL except obs, done. */
+typedef struct RlrStepOut {
+    float*   obs;            /* [n][nobs]  observation after the step (after auto-reset for finished envs) */
+    float*   reward;         /* [n] f32 (what SB3 stores) */
+    double*  reward64;       /* [n] f64 (what Rocket*.step returns) */
+    uint8_t* done;           /* [n] */
+    uint8_t* truncated;      /* [n] info["TimeLimit.truncated"] */
+    float*   terminal_obs;   /* [n][nobs]  info["terminal_observation"], written for finished envs only */
+    double*  fin_ret;        /* [n] info["episode"]["r"] for finished envs */
+    int32_t* fin_len;        /* [n] info["episode"]["l"] for finished envs */
+    uint8_t* flags;          /* [n] bit0 bounds_violation, bit1 landed, bit2 ground event, bit3 integrator failed */
+    int32_t* natt;           /* [n] RK45 attempts spent in this step (nfev = 2 + 6*natt) */
+    void*    y_pre_reset;    /* [ndim][n] state after the step, before auto-reset (same dtype as y) */
+    double*  reward_terms;   /* [6][n] velocity_tracking, thrust_penalty, eta, attitude_constraint, attitude_hint, rew_goal */
+    unsigned long long* stats; /* [RLR_NSTATS] device accumulators, atomically added (see below) */
+} RlrStepOut;
+
+/* stats slots (all u64; returns / lengths are fixed point) */
+enum {
+    RLR_STAT_STEPS = 0,      /* env steps executed */
+    RLR_STAT_ATTEMPTS = 1,   /* RK45 attempts (for the flop count: 540 + 1530*k per 6DOF step) */
+    RLR_STAT_DONE = 2,       /* finished episodes */
+    RLR_STAT_LANDED = 3,
+    RLR_STAT_VIOL = 4,
+    RLR_STAT_TRUNC = 5,
+    RLR_STAT_LEN_SUM = 6,    /* sum of finished-episode lengths */
+    RLR_STAT_RET_SUM = 7,    /* sum of finished-episode returns, as (int64)(ret * 2^20) two's complement */
+    RLR_NSTATS = 8
+};
+
+int         rlr_abi_version(void);
+const char* rlr_last_error(void);
+int         rlr_sizeof_params(void);
+
+/* Number of state / action / observation components for a params block. */
+int rlr_ndim(const RlrParams* p);
+int rlr_nact(const RlrParams* p);
+int rlr_nobs(const RlrParams* p);
+
+/* reset: (re)initialise environments.  mask NULL = all; ic_inject NULL = Philox IC keyed by
+ * (seed, env_offset + i, episode[i]); otherwise f32 [n][ndim] initial conditions to use verbatim. */
+int rlr_reset(const RlrParams* p, int precision, RlrState st, const uint8_t* mask, const float* ic_inject,
+              float* obs, int64_t n, int64_t env_offset, uint64_t seed, void* stream);
+
+/* one environment step for n environments, TimeLimit + auto-reset fused */
+int rlr_step(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind,
+             const float* ic_inject, RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed, void* stream);
+
+/* T fused steps.  actions: [T][n][nact] (or i64 [T][n] for discrete).  Outputs, when non-NULL, are
+ * [T][n][...] rollout buffers (obs/reward/done/truncated) -- the layout SB3's RolloutBuffer uses. */
+int rlr_rollout(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind,
+                int32_t T, float* obs_buf, float* reward_buf, uint8_t* done_buf, uint8_t* trunc_buf, float* last_obs,
+                unsigned long long* stats, int64_t n, int64_t env_offset, uint64_t seed, void* stream);
+
+/* FP64 / FP32 FMA roofline calibration: launches a dependent-chain FMA kernel, returns flops issued. */
+int rlr_fma_peak(int precision, int blocks, int threads, int iters, double* sink, double* flops_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RL_ROCKET_B200_H */

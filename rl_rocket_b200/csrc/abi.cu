@@ -1,0 +1,112 @@
+// abi.cu -- the extern "C" boundary declared in include/rl_rocket_b200.h.
+// No torch types, no allocation, no synchronisation: raw device pointers in, kernels enqueued on the caller's stream.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "rl_rocket_b200.h"
+
+#define RLR_DECLARE_LAUNCHERS(NS)                                                                                                          \
+    namespace NS {                                                                                                                         \
+    int launch_step(const RlrParams*, RlrState, const void*, int, const float*, RlrStepOut, int64_t, int64_t, uint64_t, cudaStream_t);    \
+    int launch_reset(const RlrParams*, RlrState, const uint8_t*, const float*, float*, int64_t, int64_t, uint64_t, cudaStream_t);         \
+    int launch_rollout(const RlrParams*, RlrState, const void*, int, int, float*, float*, uint8_t*, uint8_t*, float*, unsigned long long*, \
+                       int64_t, int64_t, uint64_t, cudaStream_t);                                                                          \
+    }
+RLR_DECLARE_LAUNCHERS(rlr_exact)
+RLR_DECLARE_LAUNCHERS(rlr_fast)
+
+namespace rlr_peak {
+int launch_fma_peak(int precision, int blocks, int threads, int iters, double* sink, double* flops_out, cudaStream_t stream);
+}
+
+static thread_local char g_err[256] = "";
+
+static int fail(int code, const char* msg) {
+    snprintf(g_err, sizeof(g_err), "%s", msg);
+    return code;
+}
+static int cuda_status(int err) {
+    if (err == 0) return RLR_OK;
+    snprintf(g_err, sizeof(g_err), "CUDA error %d: %s", err, cudaGetErrorString((cudaError_t)err));
+    return RLR_E_CUDA;
+}
+static int check_params(const RlrParams* p) {
+    if (p == nullptr) return fail(RLR_E_INVALID, "params is NULL");
+    if (p->dof != 6 && p->dof != 3 && p->dof != 1) return fail(RLR_E_INVALID, "dof must be 6, 3 or 1");
+    if (p->dt_ms <= 0 || !(p->dt > 0)) return fail(RLR_E_INVALID, "timestep must be a positive whole number of milliseconds");
+    if (p->n_discrete < 0 || p->n_discrete > RLR_MAX_DISCRETE) return fail(RLR_E_INVALID, "n_discrete out of range");
+    return RLR_OK;
+}
+static int check_state(const RlrState& st) {
+    if (!st.y || !st.k || !st.episode || !st.v0 || !st.ep_ret) return fail(RLR_E_INVALID, "RlrState has a NULL pointer");
+    return RLR_OK;
+}
+
+extern "C" {
+
+int rlr_abi_version(void) { return RLR_ABI_VERSION; }
+const char* rlr_last_error(void) { return g_err; }
+int rlr_sizeof_params(void) { return (int)sizeof(RlrParams); }
+int rlr_ndim(const RlrParams* p) { return p->dof == 6 ? 14 : 7; }
+int rlr_nact(const RlrParams* p) { return p->dof == 6 ? 3 : (p->dof == 3 ? 2 : 1); }
+int rlr_nobs(const RlrParams* p) { return p->dof == 6 ? 14 : (p->dof == 3 ? 7 : 2); }
+
+int rlr_reset(const RlrParams* p, int precision, RlrState st, const uint8_t* mask, const float* ic_inject, float* obs, int64_t n,
+              int64_t env_offset, uint64_t seed, void* stream) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (n < 0) return fail(RLR_E_INVALID, "n < 0");
+    if (n == 0) return RLR_OK;            /* empty batch: nothing to do (zero-size buffers may be NULL) */
+    if ((rc = check_state(st))) return rc;
+    if (precision != RLR_F64) return fail(RLR_E_UNSUPPORTED, "only RLR_F64 state is implemented");
+    return cuda_status(rlr_exact::launch_reset(p, st, mask, ic_inject, obs, n, env_offset, seed, (cudaStream_t)stream));
+}
+
+int rlr_step(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind, const float* ic_inject,
+             RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed, void* stream) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (n < 0) return fail(RLR_E_INVALID, "n < 0");
+    if (n == 0) return RLR_OK;
+    if ((rc = check_state(st))) return rc;
+    if (precision != RLR_F64) return fail(RLR_E_UNSUPPORTED, "only RLR_F64 state is implemented");
+    if (!actions || !out.obs || !out.done) return fail(RLR_E_INVALID, "actions, out.obs and out.done are required");
+    if (action_kind < 0 || action_kind > 2) return fail(RLR_E_INVALID, "bad action_kind");
+    if (action_kind == RLR_ACT_DISCRETE && (p->dof != 3 || p->n_discrete <= 0))
+        return fail(RLR_E_INVALID, "discrete actions need dof == 3 and a discrete_table");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (math_mode == RLR_MATH_EXACT) return cuda_status(rlr_exact::launch_step(p, st, actions, action_kind, ic_inject, out, n, env_offset, seed, s));
+    if (math_mode == RLR_MATH_FAST) return cuda_status(rlr_fast::launch_step(p, st, actions, action_kind, ic_inject, out, n, env_offset, seed, s));
+    return fail(RLR_E_INVALID, "bad math_mode");
+}
+
+int rlr_rollout(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind, int32_t T, float* obs_buf,
+                float* reward_buf, uint8_t* done_buf, uint8_t* trunc_buf, float* last_obs, unsigned long long* stats, int64_t n,
+                int64_t env_offset, uint64_t seed, void* stream) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (n < 0 || T < 0) return fail(RLR_E_INVALID, "n < 0 or T < 0");
+    if (n == 0 || T == 0) return RLR_OK;
+    if ((rc = check_state(st))) return rc;
+    if (precision != RLR_F64) return fail(RLR_E_UNSUPPORTED, "only RLR_F64 state is implemented");
+    if (!actions) return fail(RLR_E_INVALID, "actions is NULL");
+    if (action_kind < 0 || action_kind > 2) return fail(RLR_E_INVALID, "bad action_kind");
+    if (action_kind == RLR_ACT_DISCRETE && (p->dof != 3 || p->n_discrete <= 0))
+        return fail(RLR_E_INVALID, "discrete actions need dof == 3 and a discrete_table");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (math_mode == RLR_MATH_EXACT)
+        return cuda_status(rlr_exact::launch_rollout(p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf, trunc_buf, last_obs, stats, n,
+                                                     env_offset, seed, s));
+    if (math_mode == RLR_MATH_FAST)
+        return cuda_status(rlr_fast::launch_rollout(p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf, trunc_buf, last_obs, stats, n,
+                                                    env_offset, seed, s));
+    return fail(RLR_E_INVALID, "bad math_mode");
+}
+
+int rlr_fma_peak(int precision, int blocks, int threads, int iters, double* sink, double* flops_out, void* stream) {
+    if (!sink || blocks <= 0 || threads <= 0 || threads > 1024 || iters <= 0) return fail(RLR_E_INVALID, "bad fma_peak arguments");
+    return cuda_status(rlr_peak::launch_fma_peak(precision, blocks, threads, iters, sink, flops_out, (cudaStream_t)stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,800 @@
+// rocket_kernels.cuh -- sm_100a device code of the batched RL_rocket environment step.
+//
+// Included by kernels_exact.cu (nvcc -fmad=false, RLR_EXACT=1) and kernels_fast.cu (FMA
+// contraction on, RLR_EXACT=0); each translation unit wraps it in its own namespace RLR_NS.
+//
+// One thread = one environment.  The state vector lives in registers from the load at the top
+// of the kernel to the store at the bottom, across the whole adaptive RK45 solve (scipy
+// solve_ivp semantics: initial-step heuristic, error-controlled sub-steps, FSAL, terminal
+// ground event located with Brent's method on the quartic dense output), the reward, the
+// TimeLimit and the auto-reset.
+//
+// Reference call path reproduced (Tuxliri/RL_rocket):
+//   Rocket6DOF.step  my_environment/envs/rocket_env.py:690-719  -> Simulator6DOF.step utils/simulator.py:227-257
+//   Rocket.step      my_environment/envs/rocket_env.py:150-175  -> Simulator3DOF.step utils/simulator.py:55-86
+//   solve_ivp/RK45   scipy/integrate/_ivp/{ivp.py:645-700, rk.py:14-176,541-565,715-737, common.py:63-134}
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "rl_rocket_b200.h"
+
+#ifndef RLR_NS
+#error "define RLR_NS before including rocket_kernels.cuh"
+#endif
+
+namespace RLR_NS {
+
+#define RLR_DEV __device__ __forceinline__
+
+// ------------------------------------------------------------------ numpy float32 helpers
+// numpy's SIMD float32 sin/cos for |x| < pi/4 (5-FMA Horner). Explicit fmaf:
+// these FMAs are part of the reference's arithmetic, not a contraction choice.
+RLR_DEV float np_sinf_small(float x) {
+    float x2 = __fmul_rn(x, x), r;
+    r = __fmaf_rn(0x1.7d3bbcp-19f, x2, -0x1.a06bbap-13f);
+    r = __fmaf_rn(r, x2, 0x1.11119ap-07f);
+    r = __fmaf_rn(r, x2, -0x1.555556p-03f);
+    r = __fmaf_rn(r, x2, 0.0f);
+    r = __fmaf_rn(r, x, x);
+    return r;
+}
+RLR_DEV float np_cosf_small(float x) {
+    float x2 = __fmul_rn(x, x), r;
+    r = __fmaf_rn(0x1.98e616p-16f, x2, -0x1.6c06dcp-10f);
+    r = __fmaf_rn(r, x2, 0x1.55553cp-05f);
+    r = __fmaf_rn(r, x2, -0x1.0p-01f);
+    r = __fmaf_rn(r, x2, 1.0f);
+    return r;
+}
+RLR_DEV float np_sinf(float x) { return fabsf(x) < 0.78539816f ? np_sinf_small(x) : (float)sin((double)x); }
+RLR_DEV float np_cosf(float x) { return fabsf(x) < 0.78539816f ? np_cosf_small(x) : (float)cos((double)x); }
+
+// f32 ops whose rounding is part of the reference's dtype flow: never contracted.
+RLR_DEV float fmul(float a, float b) { return __fmul_rn(a, b); }
+RLR_DEV float fadd(float a, float b) { return __fadd_rn(a, b); }
+RLR_DEV float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+// numpy float32 linalg.norm on 2..4 elements: double accumulator of f32-rounded products
+RLR_DEV float f32_norm2(float a, float b) { return __fsqrt_rn((float)((double)fmul(a, a) + (double)fmul(b, b))); }
+RLR_DEV float f32_norm3(float a, float b, float c) {
+    return __fsqrt_rn((float)(((double)fmul(a, a) + (double)fmul(b, b)) + (double)fmul(c, c)));
+}
+RLR_DEV float f32_norm4(float a, float b, float c, float d) {
+    return __fsqrt_rn((float)((((double)fmul(a, a) + (double)fmul(b, b)) + (double)fmul(c, c)) + (double)fmul(d, d)));
+}
+// 10 * |nextafter(t, +inf) - t| for t >= 0  (rk.py:120)
+RLR_DEV double min_step_at(double t) { return 10 * fabs(__longlong_as_double(__double_as_longlong(t) + 1) - t); }
+RLR_DEV double py_max(double a, double b) { return (b > a) ? b : a; }
+RLR_DEV double py_min(double a, double b) { return (b < a) ? b : a; }
+
+// ------------------------------------------------------------------ Dormand-Prince tableau
+#define A10 (1.0 / 5)
+#define A20 (3.0 / 40)
+#define A21 (9.0 / 40)
+#define A30 (44.0 / 45)
+#define A31 (-56.0 / 15)
+#define A32 (32.0 / 9)
+#define A40 (19372.0 / 6561)
+#define A41 (-25360.0 / 2187)
+#define A42 (64448.0 / 6561)
+#define A43 (-212.0 / 729)
+#define A50 (9017.0 / 3168)
+#define A51 (-355.0 / 33)
+#define A52 (46732.0 / 5247)
+#define A53 (49.0 / 176)
+#define A54 (-5103.0 / 18656)
+#define B0 (35.0 / 384)
+#define B2 (500.0 / 1113)
+#define B3 (125.0 / 192)
+#define B4 (-2187.0 / 6784)
+#define B5 (11.0 / 84)
+#define E0 (-71.0 / 57600)
+#define E2 (71.0 / 16695)
+#define E3 (-71.0 / 1920)
+#define E4 (17253.0 / 339200)
+#define E5 (-22.0 / 525)
+#define E6 (1.0 / 40)
+
+__constant__ double c_P[7][4] = {
+    {1, -8048581381.0 / 2820520608, 8663915743.0 / 2820520608, -12715105075.0 / 11282082432},
+    {0, 0, 0, 0},
+    {0, 131558114200.0 / 32700410799, -68118460800.0 / 10900136933, 87487479700.0 / 32700410799},
+    {0, -1754552775.0 / 470086768, 14199869525.0 / 1410260304, -10690763975.0 / 1880347072},
+    {0, 127303824393.0 / 49829197408, -318862633887.0 / 49829197408, 701980252875.0 / 199316789632},
+    {0, -282668133.0 / 205662961, 2019193451.0 / 616988883, -1453857185.0 / 822651844},
+    {0, 40617522.0 / 29380423, -110615467.0 / 29380423, 69997945.0 / 29380423}};
+
+// ------------------------------------------------------------------ dynamical systems
+// 6DOF: y = [r(3), v(3), q0..q3, w(3), m]   (simulator.py:259-378)
+struct Sys6 {
+    static constexpr int N = 14, EV = 0, NA = 3, NOBS = 14;
+    struct Ctx { double Tb0, Tb1, Tb2, tau1, tau2, dm; };
+
+    RLR_DEV static void make_ctx(Ctx& c, const float* u) {
+        float cy = np_cosf(u[0]), sy = np_sinf(u[0]), cz = np_cosf(u[1]), sz = np_sinf(u[1]);
+        float cycz = fmul(cy, cz), sycz = fmul(sy, cz);
+        double T = (double)u[2];
+        c.Tb0 = (double)cycz * T;        // first column of _rot_mat_thrust_to_body times thrust (simulator.py:316-318)
+        c.Tb1 = (double)sycz * T;
+        c.Tb2 = (double)sz * T;
+        c.tau1 = 15.0 * c.Tb2;           // r_T_B x T_b with r_T_B = [-15,0,0]  (simulator.py:373-378)
+        c.tau2 = -15.0 * c.Tb1;
+        c.dm = (double)fdiv(-u[2], 3531.6f);   // f32 division under NEP-50 (simulator.py:291-292)
+    }
+
+    RLR_DEV static void rhs(const Ctx& c, const double (&y)[N], double (&d)[N]) {
+        const double q0 = y[6], q1 = y[7], q2 = y[8], q3 = y[9];
+        const double wx = y[10], wy = y[11], wz = y[12];
+        // Rotation.from_quat([q1,q2,q3,q0]) normalises; as_matrix() closed form
+        const double n2 = q1 * q1 + q2 * q2 + q3 * q3 + q0 * q0;
+#if RLR_EXACT
+        const double nq = sqrt(n2);
+        const double x = q1 / nq, yy = q2 / nq, z = q3 / nq, w = q0 / nq;
+        const double inv_m = 1.0 / y[13];
+#else
+        const double rn = rsqrt(n2);
+        const double x = q1 * rn, yy = q2 * rn, z = q3 * rn, w = q0 * rn;
+        const double inv_m = 1.0 / y[13];
+#endif
+        const double x2 = x * x, y2 = yy * yy, z2 = z * z, w2 = w * w;
+        const double xy = x * yy, zw = z * w, xz = x * z, yw = yy * w, yz = yy * z, xw = x * w;
+        const double R00 = x2 - y2 - z2 + w2, R01 = 2 * (xy - zw), R02 = 2 * (xz + yw);
+        const double R10 = 2 * (xy + zw), R11 = -x2 + y2 - z2 + w2, R12 = 2 * (yz - xw);
+        const double R20 = 2 * (xz - yw), R21 = 2 * (yz + xw), R22 = -x2 - y2 + z2 + w2;
+        const double F0 = R00 * c.Tb0 + R01 * c.Tb1 + R02 * c.Tb2;
+        const double F1 = R10 * c.Tb0 + R11 * c.Tb1 + R12 * c.Tb2;
+        const double F2 = R20 * c.Tb0 + R21 * c.Tb1 + R22 * c.Tb2;
+        d[0] = y[3]; d[1] = y[4]; d[2] = y[5];
+        d[3] = inv_m * F0 + (-9.81);
+        d[4] = inv_m * F1;
+        d[5] = inv_m * F2;
+        // dq = 0.5 * OMEGA(w) . q with the un-normalised q (simulator.py:287, :362-370)
+        d[6] = 0.5 * (((-wx) * q1 + (-wy) * q2) + (-wz) * q3);
+        d[7] = 0.5 * ((wx * q0 + wz * q2) + (-wy) * q3);
+        d[8] = 0.5 * ((wy * q0 + (-wz) * q1) + wx * q3);
+        d[9] = 0.5 * ((wz * q0 + wy * q1) + (-wx) * q2);
+        // dom = Jinv . (tau - w x (J w)),  J = diag(75350.25, 6037675.13, 6037675.13)
+        const double J0 = 75350.25, J1 = 6037675.13, J2 = 6037675.13;
+        const double Jw0 = J0 * wx, Jw1 = J1 * wy, Jw2 = J2 * wz;
+        const double c0 = wy * Jw2 - wz * Jw1, c1 = wz * Jw0 - wx * Jw2, c2 = wx * Jw1 - wy * Jw0;
+        d[10] = (1.0 / J0) * (0.0 - c0);
+        d[11] = (1.0 / J1) * (c.tau1 - c1);
+        d[12] = (1.0 / J2) * (c.tau2 - c2);
+        d[13] = c.dm;
+    }
+};
+
+// 3DOF: y = [x, z, theta, vx, vz, omega, m]   (simulator.py:88-130)
+struct Sys3 {
+    static constexpr int N = 7, EV = 1, NA = 2, NOBS = 7;
+    struct Ctx { double delta, T, torque, dm; };
+
+    RLR_DEV static void make_ctx(Ctx& c, const float* u) {
+        c.delta = (double)u[0];
+        c.T = (double)u[1];
+        float ts = fmul(fmul(u[1], np_sinf(u[0])), 30.0f);   // f32 product T*sin(delta)*(x_T - x_CG)  (simulator.py:124-125)
+        c.torque = (double)ts;
+        c.dm = (double)fdiv(-u[1], 3531.6f);                  // simulator.py:126
+    }
+
+    RLR_DEV static void rhs(const Ctx& c, const double (&y)[N], double (&d)[N]) {
+        const double phi = y[2], vx = y[3], vz = y[4], mass = y[6];
+        const double v2 = vx * vx + vz * vz;
+        const double Q = (0.5 * 1.225) * v2;
+        const double A = (0.3 * Q) * 10.5;
+        double sdp, cdp, cp;
+        sincos(c.delta + phi, &sdp, &cdp);
+        cp = cos(phi);
+        // NB: drag multiplies cos(phi) on BOTH axes -- reference behaviour (simulator.py:122-123)
+        const double Acp = A * cp;
+        d[0] = vx; d[1] = vz; d[2] = y[5];
+        d[3] = ((c.T * cdp - 0.0) - Acp) / mass;
+        d[4] = ((c.T * sdp + 0.0) - Acp) / mass - 9.81;
+        d[5] = (-0.0 - c.torque) / 6.04e6;
+        d[6] = c.dm;
+    }
+};
+
+// ------------------------------------------------------------------ RK45 (scipy semantics)
+template <int N>
+RLR_DEV double rms_ratio(const double (&a)[N], const double (&s)[N]) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < N; ++i) { double q = a[i] / s[i]; acc += q * q; }
+    return sqrt(acc) / sqrt((double)N);
+}
+
+// dense-output polynomial row for component i: Q_i[c] = sum_j K[j][i] * P[j][c]
+template <int N>
+RLR_DEV void dense_row(const double (&K)[7][N], int i, double (&Q)[4]) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) acc += K[j][i] * c_P[j][c];
+        Q[c] = acc;
+    }
+}
+RLR_DEV double dense_at(const double (&Q)[4], double y_old, double t_old, double h, double t) {
+    double x = (t - t_old) / h;
+    double p0 = x, p1 = p0 * x, p2 = p1 * x, p3 = p2 * x;
+    double s = ((Q[0] * p0 + Q[1] * p1) + Q[2] * p2) + Q[3] * p3;
+    return h * s + y_old;
+}
+
+// scipy.optimize.brentq (Zeros/brentq.c), xtol = rtol = 4*eps, maxiter = 100, on the event component
+__device__ __noinline__ double brentq_event(double q0, double q1, double q2, double q3, double y_old, double t_old, double h, double xa, double xb) {
+    const double Q[4] = {q0, q1, q2, q3};
+    const double xtol = 4 * 2.220446049250313e-16, rtol = 4 * 2.220446049250313e-16;
+    double xpre = xa, xcur = xb, xblk = 0, fblk = 0, spre = 0, scur = 0;
+    double fpre = dense_at(Q, y_old, t_old, h, xpre), fcur = dense_at(Q, y_old, t_old, h, xcur);
+    if (fpre == 0) return xpre;
+    if (fcur == 0) return xcur;
+#pragma unroll 1
+    for (int it = 0; it < 100; ++it) {
+        if (fpre != 0 && fcur != 0 && (signbit(fpre) != signbit(fcur))) { xblk = xpre; fblk = fpre; spre = scur = xcur - xpre; }
+        if (fabs(fblk) < fabs(fcur)) {
+            xpre = xcur; xcur = xblk; xblk = xpre;
+            fpre = fcur; fcur = fblk; fblk = fpre;
+        }
+        double delta = (xtol + rtol * fabs(xcur)) / 2;
+        double sbis = (xblk - xcur) / 2;
+        if (fcur == 0 || fabs(sbis) < delta) return xcur;
+        if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+            double stry;
+            if (xpre == xblk) {
+                stry = -fcur * (xcur - xpre) / (fcur - fpre);
+            } else {
+                double dpre = (fpre - fcur) / (xpre - xcur);
+                double dblk = (fblk - fcur) / (xblk - xcur);
+                stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+            }
+            if (2 * fabs(stry) < fmin(fabs(spre), 3 * fabs(sbis) - delta)) { spre = scur; scur = stry; }
+            else { spre = sbis; scur = sbis; }
+        } else { spre = sbis; scur = sbis; }
+        xpre = xcur; fpre = fcur;
+        if (fabs(scur) > delta) xcur += scur;
+        else xcur += (sbis > 0 ? delta : -delta);
+        fcur = dense_at(Q, y_old, t_old, h, xcur);
+    }
+    return xcur;
+}
+
+// solve_ivp(RHS, [t0, t_bound], y, events = terminal height event) with RK45 defaults.
+// Returns status: 0 reached t_bound, 1 ground event, -1 step size underflow.
+template <class S>
+RLR_DEV int rk45_solve(const typename S::Ctx& c, double t0, double t_bound, double (&y)[S::N], int& natt) {
+    constexpr int N = S::N;
+    constexpr double rtol = 1e-3, atol = 1e-6;
+    double K[7][N];
+    S::rhs(c, y, K[0]);
+    natt = 0;
+    // ---- select_initial_step (common.py:68-134)
+    double h_abs;
+    {
+        const double interval = fabs(t_bound - t0);
+        double scale[N], y1[N], f1[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) scale[i] = atol + fabs(y[i]) * rtol;
+        const double d0 = rms_ratio<N>(y, scale);
+        const double d1 = rms_ratio<N>(K[0], scale);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        h0 = py_min(h0, interval);
+#pragma unroll
+        for (int i = 0; i < N; ++i) y1[i] = y[i] + h0 * K[0][i];
+        S::rhs(c, y1, f1);
+#pragma unroll
+        for (int i = 0; i < N; ++i) f1[i] = f1[i] - K[0][i];
+        const double d2 = rms_ratio<N>(f1, scale) / h0;
+        double h1;
+        if (d1 <= 1e-15 && d2 <= 1e-15) h1 = py_max(1e-6, h0 * 1e-3);
+        else h1 = pow(0.01 / py_max(d1, d2), 1.0 / 5.0);
+        h_abs = py_min(py_min(100 * h0, h1), interval);
+    }
+    double t = t0;
+    double min_step = min_step_at(t);
+    if (h_abs < min_step) h_abs = min_step;
+    bool rejected = false;
+    int status;
+#pragma unroll 1
+    for (;;) {
+        if (h_abs < min_step) { status = -1; break; }
+        double t_new = t + h_abs;
+        if (t_new - t_bound > 0) t_new = t_bound;
+        const double h = t_new - t;
+        h_abs = fabs(h);
+        ++natt;
+        double ys[N], y_new[N];
+        // ---- rk_step (rk.py:14-71): dy = dot(K[:s].T, a[:s]) * h
+#pragma unroll
+        for (int i = 0; i < N; ++i) ys[i] = y[i] + (K[0][i] * A10) * h;
+        S::rhs(c, ys, K[1]);
+#pragma unroll
+        for (int i = 0; i < N; ++i) ys[i] = y[i] + (K[0][i] * A20 + K[1][i] * A21) * h;
+        S::rhs(c, ys, K[2]);
+#pragma unroll
+        for (int i = 0; i < N; ++i) ys[i] = y[i] + ((K[0][i] * A30 + K[1][i] * A31) + K[2][i] * A32) * h;
+        S::rhs(c, ys, K[3]);
+#pragma unroll
+        for (int i = 0; i < N; ++i) ys[i] = y[i] + (((K[0][i] * A40 + K[1][i] * A41) + K[2][i] * A42) + K[3][i] * A43) * h;
+        S::rhs(c, ys, K[4]);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            ys[i] = y[i] + ((((K[0][i] * A50 + K[1][i] * A51) + K[2][i] * A52) + K[3][i] * A53) + K[4][i] * A54) * h;
+        S::rhs(c, ys, K[5]);
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            y_new[i] = y[i] + h * ((((K[0][i] * B0 + K[2][i] * B2) + K[3][i] * B3) + K[4][i] * B4) + K[5][i] * B5);
+        S::rhs(c, y_new, K[6]);
+        // ---- error norm (rk.py:101-107,143-144)
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const double sc = atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol;
+            const double e = ((((((K[0][i] * E0 + K[2][i] * E2) + K[3][i] * E3) + K[4][i] * E4) + K[5][i] * E5) + K[6][i] * E6) * h) / sc;
+            acc += e * e;
+        }
+        const double err = sqrt(acc) / sqrt((double)N);
+        if (err < 1) {
+            double factor = (err == 0) ? 10.0 : py_min(10.0, 0.9 * pow(err, -0.2));
+            if (rejected) factor = py_min(1.0, factor);
+            h_abs *= factor;
+            // ---- terminal event g(y) = y[EV]  (ivp.py:134-158, 678-699)
+            const double g = y[S::EV], g_new = y_new[S::EV];
+            if (((g <= 0) && (g_new >= 0)) || ((g >= 0) && (g_new <= 0))) {
+                double Q[4];
+                dense_row<N>(K, S::EV, Q);
+                const double root = brentq_event(Q[0], Q[1], Q[2], Q[3], y[S::EV], t, h, t, t_new);
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    dense_row<N>(K, i, Q);
+                    y[i] = dense_at(Q, y[i], t, h, root);
+                }
+                status = 1;
+                break;
+            }
+#pragma unroll
+            for (int i = 0; i < N; ++i) { y[i] = y_new[i]; K[0][i] = K[6][i]; }
+            t = t_new;
+            if (t - t_bound >= 0) { status = 0; break; }
+            rejected = false;
+            min_step = min_step_at(t);
+            if (h_abs < min_step) h_abs = min_step;
+        } else {
+            h_abs *= py_max(0.2, 0.9 * pow(err, -0.2));
+            rejected = true;
+        }
+    }
+    return status;
+}
+
+// ------------------------------------------------------------------ reset RNG (new; Philox4x32-10)
+RLR_DEV void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+template <int N>
+RLR_DEV void sample_ic(const RlrParams& p, uint64_t seed, int64_t env, int32_t episode, float (&ic)[N]) {
+#pragma unroll
+    for (int b = 0; b * 2 < N; ++b) {
+        uint32_t c[4] = {(uint32_t)b, (uint32_t)episode, (uint32_t)((uint64_t)env & 0xffffffffu), (uint32_t)((uint64_t)env >> 32)};
+        philox4x32_10(c, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int j = b * 2 + h;
+            if (j < N) {
+                const uint64_t bits = ((uint64_t)c[2 * h] << 32) | (uint64_t)c[2 * h + 1];
+                const double uu = (double)(bits >> 11) * 0x1.0p-53;
+                const double lo = (double)p.ic_low[j], hi = (double)p.ic_high[j];
+                ic[j] = (float)(lo + (hi - lo) * uu);
+            }
+        }
+    }
+}
+
+// reset from an f32 IC: quaternion normalised in f32 (rocket_env.py:673), v0 = f32 norm of IC velocity
+template <class S>
+RLR_DEV void reset_from_ic(const RlrParams& p, float (&ic)[S::N], double (&y)[S::N], float& v0, float (&obs)[S::N]) {
+    if constexpr (S::N == 14) {
+        const float nq = f32_norm4(ic[6], ic[7], ic[8], ic[9]);
+#pragma unroll
+        for (int i = 6; i < 10; ++i) ic[i] = fdiv(ic[i], nq);
+        v0 = f32_norm3(ic[3], ic[4], ic[5]);
+    } else {
+        v0 = f32_norm2(ic[3], ic[4]);
+    }
+#pragma unroll
+    for (int i = 0; i < S::N; ++i) { y[i] = (double)ic[i]; obs[i] = (float)((double)ic[i] / p.normalizer[i]); }
+}
+
+// ------------------------------------------------------------------ reward / termination epilogues
+struct StepRes {
+    double reward;
+    double terms[6];
+    int viol, landed, status, done;
+};
+
+// Rocket6DOF._compute_reward / _compute_vtarg / _check_attitude_limits / _check_landing / bounds
+// (rocket_env.py:825-859, 986-1014, 1036-1061); s = f32 copy of the state, u = f32 physical action.
+RLR_DEV void reward6(const RlrParams& p, const float (&s)[14], const float* u, float a_thr, float v0, int status, StepRes& o) {
+    double rh0, rh1, rh2, vh0, tau;
+    if ((double)s[0] > p.waypoint) {
+        rh0 = (double)s[0] - p.waypoint; rh1 = (double)s[1]; rh2 = (double)s[2];
+        vh0 = (double)s[3] - (-2.0); tau = 20.0;
+    } else {
+        rh0 = (double)fadd(s[0], 1.0f); rh1 = 0.0; rh2 = 0.0;
+        vh0 = (double)s[3] - (-1.0); tau = 100.0;
+    }
+    const double vh1 = (double)s[4], vh2 = (double)s[5];
+    const double nr = sqrt((rh0 * rh0 + rh1 * rh1) + rh2 * rh2);
+    const double nv = sqrt((vh0 * vh0 + vh1 * vh1) + vh2 * vh2);
+    const double t_go = nr / nv;
+    const double den = py_max(1e-3, nr);
+    const double fac = 1 - exp(-t_go / tau);
+    const double mv0 = (double)(-v0);
+    const double d0 = (double)s[3] - (mv0 * (rh0 / den)) * fac;
+    const double d1 = (double)s[4] - (mv0 * (rh1 / den)) * fac;
+    const double d2 = (double)s[5] - (mv0 * (rh2 / den)) * fac;
+    // Rotation.from_quat(roll(q_f32,-1)).as_euler("zyx")
+    const double q0 = s[6], q1 = s[7], q2 = s[8], q3 = s[9];
+    const double nq = sqrt(((q1 * q1 + q2 * q2) + q3 * q3) + q0 * q0);
+    const double x = q1 / nq, yy = q2 / nq, z = q3 / nq, w = q0 / nq;
+    const double R00 = x * x - yy * yy - z * z + w * w, R01 = 2 * (x * yy - z * w), R02 = 2 * (x * z + yy * w);
+    const double R12 = 2 * (yy * z - x * w), R22 = -x * x - yy * yy + z * z + w * w;
+    const double ang0 = atan2(-R01, R00);
+    const double ang1 = asin(fmin(1.0, fmax(-1.0, R02)));
+    const double ang2 = atan2(-R12, R22);
+    const int att_viol = (fabs(ang0) > p.att_traj_limit[0]) | (fabs(ang1) > p.att_traj_limit[1]) | (fabs(ang2) > p.att_traj_limit[2]);
+    const int att_ok = (fabs(ang0) < p.att_land_limit[0]) | (fabs(ang1) < p.att_land_limit[1]) | (fabs(ang2) < p.att_land_limit[2]);
+    const int om_ok = ((double)fabsf(s[10]) < p.omega_lim[0]) | ((double)fabsf(s[11]) < p.omega_lim[1]) | ((double)fabsf(s[12]) < p.omega_lim[2]);
+    const float rn = f32_norm3(s[0], s[1], s[2]), vn = f32_norm3(s[3], s[4], s[5]);
+    const int landed = (s[0] <= 1e-3f) && ((double)vn < p.maximum_velocity) && ((double)rn < p.landing_radius) && att_ok && om_ok;
+    int inside = 1;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) inside = inside && (s[i] >= p.pos_low[i]) && (s[i] <= p.pos_high[i]);
+    const int viol = !inside;
+    o.terms[0] = p.alfa * sqrt((d0 * d0 + d1 * d1) + d2 * d2);
+    o.terms[1] = (double)fmul((float)p.beta, u[2]);
+    o.terms[2] = p.eta;
+    o.terms[3] = p.gamma * (double)att_viol;
+    o.terms[4] = 0.0;
+    o.terms[5] = p.kappa * (double)landed;
+    double r = (((o.terms[0] + o.terms[1]) + o.terms[2]) + o.terms[3]) + o.terms[5];
+    if (viol) r += -50.0;
+    if (p.reward_mode == 1) {               // RewardAnnealing (wrappers.py:68-86)
+        const float tp = fmul((float)(-p.xi), fadd(a_thr, 1.0f));
+        r = (o.terms[3] + o.terms[5]) + (double)tp;
+        o.terms[1] = (double)tp;
+    }
+    o.reward = r; o.viol = viol; o.landed = landed; o.status = status;
+    o.done = (status != 0) || viol;
+}
+
+// Rocket._compute_reward / _compute_vtarg / _check_landing / _check_bounds (rocket_env.py:177-247, 431-476)
+RLR_DEV void reward3(const RlrParams& p, const float (&s)[7], const float* u, float a_thr, float v0, int status, StepRes& o) {
+    double rh0, rh1, vh1, tau;
+    if ((double)s[1] > p.waypoint) {
+        rh0 = (double)s[0]; rh1 = (double)s[1] - p.waypoint; vh1 = (double)s[4] - (-2.0); tau = 20.0;
+    } else {
+        rh0 = 0.0; rh1 = (double)s[1]; vh1 = (double)s[4] - (-1.0); tau = 100.0;
+    }
+    const double vh0 = (double)s[3];
+    const double nr = sqrt(rh0 * rh0 + rh1 * rh1);
+    const double nv = sqrt(vh0 * vh0 + vh1 * vh1);
+    const double t_go = nr / nv;
+    const double den = py_max(1e-3, nr);
+    const double fac = 1 - exp(-t_go / tau);
+    const double mv0 = (double)(-v0);
+    const double d0 = (double)s[3] - (mv0 * (rh0 / den)) * fac;
+    const double d1 = (double)s[4] - (mv0 * (rh1 / den)) * fac;
+    const float zeta = fadd(s[2], -1.5707963267948966f);
+    const float az = fabsf(zeta);
+    const float rn = f32_norm2(s[0], s[1]), vn = f32_norm2(s[3], s[4]);
+    const int landed = (s[1] <= 1e-3f) && (vn < 15.0f) && ((double)rn < p.landing_radius) && (az < 0.2f) && (fabsf(s[5]) < 0.2f);
+    const int viol = ((double)s[0] <= p.x_left) || ((double)s[0] >= p.x_right) || ((double)s[1] >= p.y_up);
+    const float hint_arg = fadd(az, -1.5707963267948966f);
+    float hint = hint_arg > 0.0f ? hint_arg : 0.0f;
+    if (hint_arg != hint_arg) hint = hint_arg;
+    o.terms[0] = p.alfa * sqrt(d0 * d0 + d1 * d1);
+    o.terms[1] = (double)fmul((float)p.beta, u[1]);
+    o.terms[2] = p.eta;
+    o.terms[3] = p.gamma * (double)(az > 6.283185307179586f);
+    o.terms[4] = (double)fmul((float)p.delta, hint);
+    o.terms[5] = p.kappa * (double)landed;
+    double r = ((((o.terms[0] + o.terms[1]) + o.terms[2]) + o.terms[3]) + o.terms[4]) + o.terms[5];
+    if (viol) r += -50.0;
+    if (p.reward_mode == 1) {               // python float + np.float32 -> f32 arithmetic
+        const float tp = fmul((float)(-p.xi), fadd(a_thr, 1.0f));
+        const float rr = fadd((float)(o.terms[3] + o.terms[5]), tp);
+        r = (double)rr;
+        o.terms[1] = (double)tp;
+    }
+    o.reward = r; o.viol = viol; o.landed = landed; o.status = status;
+    o.done = (status != 0) || viol;
+}
+
+// ------------------------------------------------------------------ one environment step in registers
+template <class S>
+struct EnvState {
+    double y[S::N];
+    int32_t k, episode;
+    float v0;
+    double ep_ret;
+};
+
+// action -> physical f32 u (+ the normalised throttle for RewardAnnealing)
+template <class S>
+RLR_DEV void map_action(const RlrParams& p, const void* actions, int action_kind, int64_t i, float (&u)[3], float& a_thr) {
+    a_thr = 0.0f;
+    if constexpr (S::N == 14) {
+        const float* a = (const float*)actions + i * 3;
+        const float a0 = a[0], a1 = a[1], a2 = a[2];
+        if (action_kind == RLR_ACT_NORMALIZED) {
+            u[0] = (float)((double)a0 * p.max_gimbal);
+            u[1] = (float)((double)a1 * p.max_gimbal);
+            u[2] = fmul(fdiv(fadd(a2, 1.0f), 2.0f), p.max_thrust);
+            a_thr = a2;
+        } else { u[0] = a0; u[1] = a1; u[2] = a2; }
+    } else {
+        float a0, a1;
+        if (action_kind == RLR_ACT_DISCRETE) {
+            long long idx = ((const long long*)actions)[i];
+            idx = idx < 0 ? 0 : (idx >= p.n_discrete ? p.n_discrete - 1 : idx);
+            u[0] = p.discrete_table[2 * idx]; u[1] = p.discrete_table[2 * idx + 1]; u[2] = 0.0f;
+            return;
+        }
+        if (p.dof == 1) { a0 = 0.0f; a1 = ((const float*)actions)[i]; }
+        else { const float* a = (const float*)actions + i * 2; a0 = a[0]; a1 = a[1]; }
+        if (action_kind == RLR_ACT_NORMALIZED) {
+            u[0] = (float)((double)a0 * p.max_gimbal);
+            u[1] = fmul(fdiv(fadd(a1, 1.0f), 2.0f), p.max_thrust);
+            a_thr = a1;
+        } else { u[0] = a0; u[1] = a1; }
+        u[2] = 0.0f;
+    }
+}
+
+struct StepFlags { int done, trunc, viol, landed, status, natt; };
+
+// Integrate one env step, compute reward/obs/flags.  `st` is updated to the post-step state
+// (NOT reset).  obs = observation of the post-step state.
+template <class S>
+RLR_DEV void env_step(const RlrParams& p, EnvState<S>& st, const float (&u)[3], float a_thr, float (&obs)[S::N], StepRes& res, StepFlags& fl) {
+    typename S::Ctx c;
+    S::make_ctx(c, u);
+    const double t = (double)((long long)st.k * (long long)p.dt_ms) / 1000.0;   // round(t + dt, 3)  (simulator.py:245)
+    int natt;
+    const int status = rk45_solve<S>(c, t, t + p.dt, st.y, natt);
+    float s[S::N];
+    if constexpr (S::N == 14) {
+        const double nq = sqrt(((st.y[6] * st.y[6] + st.y[7] * st.y[7]) + st.y[8] * st.y[8]) + st.y[9] * st.y[9]);
+#pragma unroll
+        for (int i = 6; i < 10; ++i) st.y[i] = st.y[i] / nq;        // simulator.py:250
+#pragma unroll
+        for (int i = 0; i < S::N; ++i) { s[i] = (float)st.y[i]; obs[i] = (float)(st.y[i] / p.normalizer[i]); }   // rocket_env.py:695, :963-964
+        reward6(p, (const float(&)[14])s, u, a_thr, st.v0, status, res);
+    } else {
+        const double pi2 = 2.0 * 3.141592653589793;
+        st.y[2] = fmod(fmod(st.y[2], pi2) + pi2, pi2);                // simulator.py:77, :150-163
+#pragma unroll
+        for (int i = 0; i < S::N; ++i) { s[i] = (float)st.y[i]; obs[i] = (float)((double)s[i] / p.normalizer[i]); }   // rocket_env.py:155,:175,:209-210
+        reward3(p, (const float(&)[7])s, u, a_thr, st.v0, status, res);
+    }
+    st.k += 1;
+    st.ep_ret += res.reward;
+    fl.trunc = 0;
+    fl.done = res.done;
+    if (p.max_episode_steps > 0 && st.k >= p.max_episode_steps) { fl.trunc = !res.done; fl.done = 1; }   // gym TimeLimit
+    fl.viol = res.viol; fl.landed = res.landed; fl.status = status; fl.natt = natt;
+}
+
+// ------------------------------------------------------------------ kernels
+template <class S>
+RLR_DEV void load_state(const RlrState& gs, int64_t n, int64_t i, EnvState<S>& st) {
+    const double* y = (const double*)gs.y;
+#pragma unroll
+    for (int c = 0; c < S::N; ++c) st.y[c] = y[c * n + i];
+    st.k = gs.k[i]; st.episode = gs.episode[i]; st.v0 = gs.v0[i]; st.ep_ret = gs.ep_ret[i];
+}
+template <class S>
+RLR_DEV void store_state(const RlrState& gs, int64_t n, int64_t i, const EnvState<S>& st) {
+    double* y = (double*)gs.y;
+#pragma unroll
+    for (int c = 0; c < S::N; ++c) y[c * n + i] = st.y[c];
+    gs.k[i] = st.k; gs.episode[i] = st.episode; gs.v0[i] = st.v0; gs.ep_ret[i] = st.ep_ret;
+}
+
+template <class S>
+RLR_DEV void write_obs(const RlrParams& p, float* dst, int64_t i, const float (&obs)[S::N]) {
+    if (p.dof == 1) { dst[i * 2] = obs[1]; dst[i * 2 + 1] = obs[4]; }
+    else {
+#pragma unroll
+        for (int c = 0; c < S::N; ++c) dst[i * S::N + c] = obs[c];
+    }
+}
+
+// warp-shuffle reduction of the episode statistics, one atomic per warp and slot
+RLR_DEV void accumulate_stats(unsigned long long* stats, bool active, const StepFlags& fl, int ep_len, double ep_ret) {
+    if (stats == nullptr) return;
+    unsigned long long v[RLR_NSTATS];
+    v[RLR_STAT_STEPS] = active ? 1ull : 0ull;
+    v[RLR_STAT_ATTEMPTS] = active ? (unsigned long long)fl.natt : 0ull;
+    const bool fin = active && fl.done;
+    v[RLR_STAT_DONE] = fin ? 1ull : 0ull;
+    v[RLR_STAT_LANDED] = (fin && fl.landed) ? 1ull : 0ull;
+    v[RLR_STAT_VIOL] = (fin && fl.viol) ? 1ull : 0ull;
+    v[RLR_STAT_TRUNC] = (fin && fl.trunc) ? 1ull : 0ull;
+    v[RLR_STAT_LEN_SUM] = fin ? (unsigned long long)ep_len : 0ull;
+    v[RLR_STAT_RET_SUM] = fin ? (unsigned long long)(long long)llrint(ep_ret * 1048576.0) : 0ull;
+#pragma unroll
+    for (int s = 0; s < RLR_NSTATS; ++s) {
+        unsigned long long x = v[s];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+        if ((threadIdx.x & 31) == 0 && x != 0ull) atomicAdd(stats + s, x);
+    }
+}
+
+// finished-episode handling shared by step and rollout kernels: record episode info, then reset in registers
+template <class S>
+RLR_DEV void finish_and_reset(const RlrParams& p, EnvState<S>& st, const float* ic_inject, int64_t i, int64_t env_offset, uint64_t seed,
+                              float (&obs)[S::N]) {
+    st.episode += 1;
+    float ic[S::N];
+    if (ic_inject != nullptr) {
+#pragma unroll
+        for (int c = 0; c < S::N; ++c) ic[c] = ic_inject[i * S::N + c];
+    } else {
+        sample_ic<S::N>(p, seed, env_offset + i, st.episode, ic);
+    }
+    reset_from_ic<S>(p, ic, st.y, st.v0, obs);
+    st.k = 0;
+    st.ep_ret = 0.0;
+}
+
+template <class S>
+__global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ RlrParams p, RlrState gs, const void* actions, int action_kind,
+                                                   const float* ic_inject, RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n;
+    StepFlags fl = {0, 0, 0, 0, 0, 0};
+    int ep_len = 0;
+    double ep_ret = 0.0;
+    if (active) {
+        EnvState<S> st;
+        load_state<S>(gs, n, i, st);
+        float u[3], a_thr;
+        map_action<S>(p, actions, action_kind, i, u, a_thr);
+        float obs[S::N];
+        StepRes res;
+        env_step<S>(p, st, u, a_thr, obs, res, fl);
+        ep_len = st.k; ep_ret = st.ep_ret;
+        if (out.reward) out.reward[i] = (float)res.reward;
+        if (out.reward64) out.reward64[i] = res.reward;
+        out.done[i] = (uint8_t)fl.done;
+        if (out.truncated) out.truncated[i] = (uint8_t)fl.trunc;
+        if (out.natt) out.natt[i] = fl.natt;
+        if (out.flags) out.flags[i] = (uint8_t)((fl.viol ? 1 : 0) | (fl.landed ? 2 : 0) | (fl.status == 1 ? 4 : 0) | (fl.status < 0 ? 8 : 0));
+        if (out.reward_terms) {
+#pragma unroll
+            for (int c = 0; c < 6; ++c) out.reward_terms[c * n + i] = res.terms[c];
+        }
+        if (out.y_pre_reset) {
+            double* yp = (double*)out.y_pre_reset;
+#pragma unroll
+            for (int c = 0; c < S::N; ++c) yp[c * n + i] = st.y[c];
+        }
+        if (fl.done) {
+            if (out.terminal_obs) write_obs<S>(p, out.terminal_obs, i, obs);
+            if (out.fin_ret) out.fin_ret[i] = st.ep_ret;
+            if (out.fin_len) out.fin_len[i] = st.k;
+            finish_and_reset<S>(p, st, ic_inject, i, env_offset, seed, obs);
+        }
+        write_obs<S>(p, out.obs, i, obs);
+        store_state<S>(gs, n, i, st);
+    }
+    accumulate_stats(out.stats, active, fl, ep_len, ep_ret);
+}
+
+template <class S>
+__global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ RlrParams p, RlrState gs, const uint8_t* mask, const float* ic_inject,
+                                                    float* obs_out, int64_t n, int64_t env_offset, uint64_t seed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (mask != nullptr && mask[i] == 0) return;
+    EnvState<S> st;
+    st.episode = gs.episode[i];
+    float ic[S::N], obs[S::N];
+    if (ic_inject != nullptr) {
+#pragma unroll
+        for (int c = 0; c < S::N; ++c) ic[c] = ic_inject[i * S::N + c];
+    } else {
+        sample_ic<S::N>(p, seed, env_offset + i, st.episode, ic);
+    }
+    reset_from_ic<S>(p, ic, st.y, st.v0, obs);
+    st.k = 0; st.ep_ret = 0.0;
+    if (obs_out) write_obs<S>(p, obs_out, i, obs);
+    store_state<S>(gs, n, i, st);
+}
+
+// T fused steps: state stays in registers between env steps; per-step outputs go to [T][n][..] rollout buffers
+template <class S>
+__global__ void __launch_bounds__(128) rollout_kernel(const __grid_constant__ RlrParams p, RlrState gs, const void* actions, int action_kind, int T,
+                                                      float* obs_buf, float* reward_buf, uint8_t* done_buf, uint8_t* trunc_buf, float* last_obs,
+                                                      unsigned long long* stats, int64_t n, int64_t env_offset, uint64_t seed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < n;
+    EnvState<S> st;
+    if (active) load_state<S>(gs, n, i, st);
+    const int na = (p.dof == 1) ? 1 : S::NA;
+    const int no = (p.dof == 1) ? 2 : S::NOBS;
+    float obs[S::N];
+#pragma unroll 1
+    for (int t = 0; t < T; ++t) {
+        StepFlags fl = {0, 0, 0, 0, 0, 0};
+        int ep_len = 0;
+        double ep_ret = 0.0;
+        if (active) {
+            const void* a_t = (action_kind == RLR_ACT_DISCRETE) ? (const void*)((const long long*)actions + (int64_t)t * n)
+                                                                : (const void*)((const float*)actions + (int64_t)t * n * na);
+            float u[3], a_thr;
+            map_action<S>(p, a_t, action_kind, i, u, a_thr);
+            StepRes res;
+            env_step<S>(p, st, u, a_thr, obs, res, fl);
+            ep_len = st.k; ep_ret = st.ep_ret;
+            if (fl.done) finish_and_reset<S>(p, st, nullptr, i, env_offset, seed, obs);
+            if (obs_buf) write_obs<S>(p, obs_buf + (int64_t)t * n * no, i, obs);
+            if (reward_buf) reward_buf[(int64_t)t * n + i] = (float)res.reward;
+            if (done_buf) done_buf[(int64_t)t * n + i] = (uint8_t)fl.done;
+            if (trunc_buf) trunc_buf[(int64_t)t * n + i] = (uint8_t)fl.trunc;
+        }
+        accumulate_stats(stats, active, fl, ep_len, ep_ret);
+    }
+    if (active) {
+        if (last_obs && T > 0) write_obs<S>(p, last_obs, i, obs);
+        store_state<S>(gs, n, i, st);
+    }
+}
+
+// ------------------------------------------------------------------ host launchers (called from abi.cu)
+inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
+
+int launch_step(const RlrParams* p, RlrState st, const void* actions, int action_kind, const float* ic_inject, RlrStepOut out, int64_t n,
+                int64_t env_offset, uint64_t seed, cudaStream_t stream) {
+    const int block = 128;
+    if (p->dof == 6) step_kernel<Sys6><<<grid_for(n, block), block, 0, stream>>>(*p, st, actions, action_kind, ic_inject, out, n, env_offset, seed);
+    else step_kernel<Sys3><<<grid_for(n, block), block, 0, stream>>>(*p, st, actions, action_kind, ic_inject, out, n, env_offset, seed);
+    return (int)cudaGetLastError();
+}
+
+int launch_reset(const RlrParams* p, RlrState st, const uint8_t* mask, const float* ic_inject, float* obs, int64_t n, int64_t env_offset,
+                 uint64_t seed, cudaStream_t stream) {
+    const int block = 128;
+    if (p->dof == 6) reset_kernel<Sys6><<<grid_for(n, block), block, 0, stream>>>(*p, st, mask, ic_inject, obs, n, env_offset, seed);
+    else reset_kernel<Sys3><<<grid_for(n, block), block, 0, stream>>>(*p, st, mask, ic_inject, obs, n, env_offset, seed);
+    return (int)cudaGetLastError();
+}
+
+int launch_rollout(const RlrParams* p, RlrState st, const void* actions, int action_kind, int T, float* obs_buf, float* reward_buf,
+                   uint8_t* done_buf, uint8_t* trunc_buf, float* last_obs, unsigned long long* stats, int64_t n, int64_t env_offset,
+                   uint64_t seed, cudaStream_t stream) {
+    const int block = 128;
+    if (p->dof == 6)
+        rollout_kernel<Sys6><<<grid_for(n, block), block, 0, stream>>>(*p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf, trunc_buf,
+                                                                       last_obs, stats, n, env_offset, seed);
+    else
+        rollout_kernel<Sys3><<<grid_for(n, block), block, 0, stream>>>(*p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf, trunc_buf,
+                                                                       last_obs, stats, n, env_offset, seed);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace RLR_NS

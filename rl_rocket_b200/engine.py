@@ -1,0 +1,153 @@
+"""RocketBatch: N environments resident on one GPU, stepped by the sm_100a kernels through the C ABI.
+
+PyTorch owns every buffer (structure-of-arrays state, row-major obs/action tensors); the library gets
+raw `data_ptr()`s and the current CUDA stream -- zero-copy, no hidden synchronisation.  This module is
+the tensor-native API (`step_tensor`, `rollout`); the gym / SB3 facades in envs.py and vec_env.py sit on top.
+"""
+import ctypes as C
+
+import torch
+
+from . import _native as N
+from .config import EnvSpec
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class RocketBatch:
+    def __init__(self, spec: EnvSpec, num_envs: int, device="cuda:0", seed=None, env_offset=0, math_mode="fast", debug_outputs=False):
+        self.lib = N.load()                      # raises if the CUDA extension is not built
+        if not torch.cuda.is_available():
+            raise RuntimeError("rl_rocket_b200 needs a CUDA device (there is no CPU fallback)")
+        self.spec = spec
+        self.n = int(num_envs)
+        self.device = torch.device(device)
+        self.seed = int(spec.seed if seed is None else seed)
+        self.env_offset = int(env_offset)
+        self.math_mode = {"exact": N.MATH_EXACT, "fast": N.MATH_FAST}[math_mode]
+        n, nd, no, dev = self.n, spec.ndim, spec.nobs, self.device
+        # persistent state (SoA)
+        self.y = torch.zeros((nd, n), dtype=torch.float64, device=dev)
+        self.k = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.episode = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.v0 = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.ep_ret = torch.zeros(n, dtype=torch.float64, device=dev)
+        # per-step outputs
+        self.obs = torch.zeros((n, no), dtype=torch.float32, device=dev)
+        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.reward64 = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.truncated = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.terminal_obs = torch.zeros((n, no), dtype=torch.float32, device=dev)
+        self.fin_ret = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.fin_len = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.flags = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.stats = torch.zeros(N.NSTATS, dtype=torch.int64, device=dev)
+        self.debug = bool(debug_outputs)
+        self.natt = torch.zeros(n, dtype=torch.int32, device=dev) if self.debug else None
+        self.y_pre_reset = torch.zeros((nd, n), dtype=torch.float64, device=dev) if self.debug else None
+        self.reward_terms = torch.zeros((6, n), dtype=torch.float64, device=dev) if self.debug else None
+        self.launches = 0
+
+    # -- raw structs -------------------------------------------------------------------------
+    def _state(self):
+        return N.RlrState(_ptr(self.y), _ptr(self.k), _ptr(self.episode), _ptr(self.v0), _ptr(self.ep_ret))
+
+    def _out(self):
+        return N.RlrStepOut(_ptr(self.obs), _ptr(self.reward), _ptr(self.reward64), _ptr(self.done), _ptr(self.truncated),
+                            _ptr(self.terminal_obs), _ptr(self.fin_ret), _ptr(self.fin_len), _ptr(self.flags), _ptr(self.natt),
+                            _ptr(self.y_pre_reset), _ptr(self.reward_terms), _ptr(self.stats))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check_actions(self, actions, leading=()):
+        spec = self.spec
+        if actions.device != self.device:
+            raise ValueError("actions must live on the environment's device")
+        if actions.dtype == torch.int64:
+            kind, shape = N.ACT_DISCRETE, (*leading, self.n)
+        elif actions.dtype == torch.float32:
+            kind, shape = None, (*leading, self.n, spec.nact)
+        else:
+            raise TypeError("actions must be float32 (continuous) or int64 (discrete)")
+        if tuple(actions.shape) != shape and not (spec.nact == 1 and tuple(actions.shape) == (*leading, self.n)):
+            raise ValueError(f"actions must have shape {shape}, got {tuple(actions.shape)}")
+        if not actions.is_contiguous():
+            actions = actions.contiguous()
+        return actions, kind
+
+    # -- API ----------------------------------------------------------------------------------
+    def reset(self, mask=None, ic=None):
+        """(Re)start environments; returns the obs tensor [n, nobs] (device).  `ic`: optional f32 [n, ndim] initial conditions."""
+        with torch.cuda.device(self.device):
+            if ic is not None:
+                ic = torch.as_tensor(ic, dtype=torch.float32, device=self.device).contiguous()
+                assert tuple(ic.shape) == (self.n, self.spec.ndim)
+            if mask is not None:
+                mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            N.check(self.lib.rlr_reset(C.byref(self.spec.params), N.F64, self._state(), _ptr(mask), _ptr(ic), _ptr(self.obs),
+                                       self.n, self.env_offset, self.seed, self._stream()))
+            self.launches += 1
+        return self.obs
+
+    def step_tensor(self, actions, physical=False, ic_inject=None):
+        """One step for all envs.  actions: cuda f32 [n, nact] (or i64 [n] discrete).  Returns (obs, reward, done) device tensors
+        (views of persistent buffers, overwritten by the next call)."""
+        actions, kind = self._check_actions(actions)
+        if kind is None:
+            kind = N.ACT_PHYSICAL if physical else N.ACT_NORMALIZED
+        with torch.cuda.device(self.device):
+            if ic_inject is not None:
+                ic_inject = torch.as_tensor(ic_inject, dtype=torch.float32, device=self.device).contiguous()
+            N.check(self.lib.rlr_step(C.byref(self.spec.params), N.F64, self.math_mode, self._state(), _ptr(actions), kind,
+                                      _ptr(ic_inject), self._out(), self.n, self.env_offset, self.seed, self._stream()))
+            self.launches += 1
+        return self.obs, self.reward, self.done
+
+    def rollout(self, actions, obs_buf=None, reward_buf=None, done_buf=None, trunc_buf=None, physical=False):
+        """T fused steps in ONE launch.  actions: cuda f32 [T, n, nact] (or i64 [T, n]); optional [T, n, ...] output buffers."""
+        T = actions.shape[0]
+        actions, kind = self._check_actions(actions, leading=(T,))
+        if kind is None:
+            kind = N.ACT_PHYSICAL if physical else N.ACT_NORMALIZED
+        with torch.cuda.device(self.device):
+            N.check(self.lib.rlr_rollout(C.byref(self.spec.params), N.F64, self.math_mode, self._state(), _ptr(actions), kind, T,
+                                         _ptr(obs_buf), _ptr(reward_buf), _ptr(done_buf), _ptr(trunc_buf), _ptr(self.obs),
+                                         _ptr(self.stats), self.n, self.env_offset, self.seed, self._stream()))
+            self.launches += 1
+        return self.obs
+
+    def read_stats(self, reset=False):
+        """Episode statistics accumulated on the device by warp-shuffle reductions (host sync)."""
+        v = self.stats.cpu().tolist()
+        if reset:
+            self.stats.zero_()
+        d = dict(zip(N.STAT_NAMES, v))
+        d["ret_sum"] = d.pop("ret_sum_fx") / 1048576.0
+        return d
+
+
+def fma_peak(precision="f64", device="cuda:0", blocks=None, threads=256, iters=4096, repeats=5):
+    """Measured FMA roofline (Tflop/s) of the device: the denominator for roofline.frac (MEASURED_PEAKS.json has no ALU figure)."""
+    lib = N.load()
+    dev = torch.device(device)
+    with torch.cuda.device(dev):
+        props = torch.cuda.get_device_properties(dev)
+        blocks = blocks or props.multi_processor_count * 8
+        sink = torch.zeros(8, dtype=torch.float64, device=dev)
+        flops = C.c_double(0)
+        prec = N.F64 if precision == "f64" else N.F32
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        best = 0.0
+        for r in range(repeats + 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            N.check(lib.rlr_fma_peak(prec, blocks, threads, iters, _ptr(sink), C.byref(flops), stream))
+            e1.record()
+            e1.synchronize()
+            if r >= 2:
+                best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best

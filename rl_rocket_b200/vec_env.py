@@ -1,0 +1,177 @@
+"""RocketVecEnv: a stable-baselines3-compatible vectorised environment whose `step` is ONE kernel launch.
+
+Replaces `DummyVecEnv([lambda: Monitor(TimeLimit(Rocket6DOF(**cfg)))])` (main_6DOF.py:21-22, :71; main.py:65-70, :105):
+TimeLimit truncation, Monitor's per-episode return/length and DummyVecEnv's auto-reset + `terminal_observation`
+are fused into the step kernel.  API = SB3 1.6 `VecEnv` (reset / step_async / step_wait / step / close / seed /
+get_attr / set_attr / env_method / env_is_wrapped / render / get_images) plus a tensor-native fast path:
+
+    obs, reward, done = venv.step_tensor(actions_cuda)      # no host sync
+    obs, reward, done = venv.step_host(actions_pinned)      # pinned host buffers in/out, one H2D + one D2H per step
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import spaces
+from .config import DEFAULT_DISCRETE_TABLE, EnvSpec
+from .engine import RocketBatch
+
+try:  # pragma: no cover - SB3 is absent from the build image
+    from stable_baselines3.common.vec_env.base_vec_env import VecEnv as _VecEnvBase
+except Exception:  # noqa: BLE001
+    class _VecEnvBase:
+        def __init__(self, num_envs, observation_space, action_space):
+            self.num_envs, self.observation_space, self.action_space = num_envs, observation_space, action_space
+
+        def step(self, actions):
+            self.step_async(actions)
+            return self.step_wait()
+
+        @property
+        def unwrapped(self):
+            return self
+
+
+class _LazyInfos(list):
+    """list[dict] of length num_envs built without O(N) Python work: all non-terminal envs share one empty dict."""
+
+
+class RocketVecEnv(_VecEnvBase):
+    def __init__(self, num_envs, dof=6, max_episode_steps=None, device="cuda:0", discrete_actions=False, discrete_table=None,
+                 reward_annealing=False, math_mode="fast", env_offset=0, **env_kwargs):
+        table = (discrete_table or DEFAULT_DISCRETE_TABLE) if discrete_actions else None
+        self.spec = EnvSpec(dof, max_episode_steps=max_episode_steps or 0, reward_mode=1 if reward_annealing else 0,
+                            discrete_table=table, **env_kwargs)
+        self.batch = RocketBatch(self.spec, num_envs, device=device, math_mode=math_mode, env_offset=env_offset)
+        obs_space = spaces.Box(low=-1, high=1, shape=(self.spec.nobs,))
+        act_space = spaces.Discrete(len(table)) if discrete_actions else spaces.Box(low=-1, high=1, shape=(self.spec.nact,))
+        super().__init__(num_envs, obs_space, act_space)
+        self.discrete = bool(discrete_actions)
+        self.device = self.batch.device
+        n, no = num_envs, self.spec.nobs
+        # pinned host mirrors for the numpy-facing API (one packed D2H per step)
+        self._h_actions = torch.zeros((n,) if self.discrete else (n, self.spec.nact),
+                                      dtype=torch.int64 if self.discrete else torch.float32).pin_memory()
+        self._d_actions = torch.zeros_like(self._h_actions, device=self.device)
+        self._h_obs = torch.zeros((n, no), dtype=torch.float32).pin_memory()
+        self._h_rew = torch.zeros(n, dtype=torch.float32).pin_memory()
+        self._h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        self._t_start = time.time()
+        self._pending = False
+        self.metadata = {"render.modes": []}
+
+    # ---------------------------------------------------------------- tensor-native fast path
+    def reset_tensor(self):
+        return self.batch.reset()
+
+    def step_tensor(self, actions):
+        return self.batch.step_tensor(actions)
+
+    def rollout_tensor(self, actions, obs_buf=None, reward_buf=None, done_buf=None, trunc_buf=None):
+        return self.batch.rollout(actions, obs_buf, reward_buf, done_buf, trunc_buf)
+
+    def step_host(self, actions_host):
+        """actions: pinned host tensor (or numpy array).  Returns pinned host tensors (obs, reward, done) -- views of
+        persistent buffers.  H2D of the actions and D2H of the results are inside this call."""
+        if not torch.is_tensor(actions_host):
+            actions_host = torch.as_tensor(np.ascontiguousarray(actions_host))
+        self._d_actions.copy_(actions_host.reshape(self._d_actions.shape), non_blocking=True)
+        b = self.batch
+        b.step_tensor(self._d_actions)
+        self._h_obs.copy_(b.obs, non_blocking=True)
+        self._h_rew.copy_(b.reward, non_blocking=True)
+        self._h_done.copy_(b.done, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._h_obs, self._h_rew, self._h_done
+
+    def h2d_bytes_per_step(self):
+        return self._h_actions.numel() * self._h_actions.element_size()
+
+    def d2h_bytes_per_step(self):
+        return sum(t.numel() * t.element_size() for t in (self._h_obs, self._h_rew, self._h_done))
+
+    # ---------------------------------------------------------------- SB3 VecEnv API
+    def reset(self):
+        obs = self.batch.reset()
+        return obs.cpu().numpy()
+
+    def step_async(self, actions):
+        a = np.asarray(actions)
+        if self.discrete:
+            self._h_actions.copy_(torch.as_tensor(a.astype(np.int64).reshape(-1)))
+        else:
+            self._h_actions.copy_(torch.as_tensor(a.astype(np.float32).reshape(self.num_envs, -1)))
+        self._pending = True
+
+    def step_wait(self):
+        assert self._pending, "step_wait() without step_async()"
+        self._pending = False
+        obs, rew, done = self.step_host(self._h_actions)
+        obs_np, rew_np, done_np = obs.numpy().copy(), rew.numpy().copy(), done.numpy().astype(bool)
+        infos = _LazyInfos([_EMPTY_INFO] * self.num_envs)
+        idx = np.nonzero(done_np)[0]
+        if idx.size:
+            b = self.batch
+            sel = torch.as_tensor(idx, device=self.device)
+            term = b.terminal_obs[sel].cpu().numpy()
+            ret = b.fin_ret[sel].cpu().numpy()
+            length = b.fin_len[sel].cpu().numpy()
+            trunc = b.truncated[sel].cpu().numpy().astype(bool)
+            flags = b.flags[sel].cpu().numpy()
+            now = round(time.time() - self._t_start, 6)
+            for j, i in enumerate(idx):
+                infos[i] = {"terminal_observation": term[j], "TimeLimit.truncated": bool(trunc[j]),
+                            "episode": {"r": round(float(ret[j]), 6), "l": int(length[j]), "t": now},
+                            "bounds_violation": bool(flags[j] & 1), "landed": bool(flags[j] & 2), "is_done": True}
+        return obs_np, rew_np, done_np, infos
+
+    def close(self):
+        pass
+
+    def seed(self, seed=None):
+        seed = 0 if seed is None else int(seed)
+        self.batch.seed = seed
+        return [seed + i for i in range(self.num_envs)]
+
+    def _indices(self, indices):
+        if indices is None:
+            return range(self.num_envs)
+        if isinstance(indices, int):
+            return [indices]
+        return indices
+
+    def get_attr(self, attr_name, indices=None):
+        src = self if hasattr(self, attr_name) else self.spec
+        return [getattr(src, attr_name) for _ in self._indices(indices)]
+
+    def set_attr(self, attr_name, value, indices=None):
+        setattr(self, attr_name, value)
+
+    def env_method(self, method_name, *args, indices=None, **kwargs):
+        return [getattr(self, method_name)(*args, **kwargs) for _ in self._indices(indices)]
+
+    def env_is_wrapped(self, wrapper_class, indices=None):
+        return [False for _ in self._indices(indices)]
+
+    def get_images(self):
+        raise NotImplementedError("rendering is outside the hot path this package replaces")
+
+    def render(self, mode="human"):
+        raise NotImplementedError("rendering is outside the hot path this package replaces")
+
+    # reference-side names reached through get_attr / wrappers
+    @property
+    def reward_coefficients(self):
+        return self.spec.reward_coeff
+
+    def set_reward_annealing(self, on=True):
+        """Second training phase of main_6DOF.py:95-103 / main.py:130-175 (RewardAnnealing) without rebuilding the envs."""
+        self.spec = self.spec.with_(reward_mode=1 if on else 0)
+        self.batch.spec = self.spec
+
+    def episode_stats(self, reset=False):
+        return self.batch.read_stats(reset=reset)
+
+
+_EMPTY_INFO = {}

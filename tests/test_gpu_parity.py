@@ -1,0 +1,209 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden vectors of the live reference and
+against the C oracle on seeded inputs.  Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+from tests import goldutil as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine():
+    from rl_rocket_b200.config import EnvSpec
+    from rl_rocket_b200.engine import RocketBatch
+    return EnvSpec, RocketBatch
+
+
+def _spec(name, **over):
+    EnvSpec, _ = _engine()
+    dof, cfgf, tl, mode, akind = G.TRAJ[name]
+    kw = dict(max_episode_steps=tl, reward_mode=mode, **cfgf())
+    if akind == "discrete":
+        kw["discrete_table"] = G.DISCRETE_TABLE
+    kw.update(over)
+    return EnvSpec(dof, **kw), akind
+
+
+@pytest.mark.parametrize("math_mode", ["exact", "fast"])
+@pytest.mark.parametrize("name", sorted(G.TRAJ))
+def test_golden_trajectories(name, math_mode):
+    """Every trajectory the live reference produced (tests/golden), replayed on the GPU with the same ICs and actions."""
+    _, RocketBatch = _engine()
+    spec, akind = _spec(name)
+    g = G.load(name)
+    T, N = g["done"].shape
+    env = RocketBatch(spec, N, seed=int(g["seed"]), math_mode=math_mode, debug_outputs=True)
+    obs0 = env.reset().cpu().numpy()
+    assert np.abs(obs0.astype(float) - g["obs0"]).max() <= G.OBS_TOL
+    norm = spec.state_normalizer
+    worst = 0.0
+    for t in range(T):
+        a = torch.as_tensor(g["actions"][t]).cuda()
+        obs, rew, done = env.step_tensor(a)
+        gs = {k: g[k][t] for k in ("done", "truncated", "nfev", "y", "reward", "obs")}
+        d, _ = G.compare_step(f"{name}/{math_mode}", t, norm, gs, env.y_pre_reset.cpu().numpy(), obs.cpu().numpy(),
+                              env.reward64.cpu().numpy(), done.cpu().numpy(), env.truncated.cpu().numpy(), env.natt.cpu().numpy())
+        dn = g["done"][t].astype(bool)
+        assert np.abs(env.terminal_obs.cpu().numpy()[dn].astype(float) - g["terminal_obs"][t][dn]).max(initial=0) <= G.OBS_TOL
+        worst = max(worst, d)
+    print(f"{name} [{math_mode}] worst normalised state deviation {worst:.3e}")
+
+
+def _oracle_pair(dof, cfg, N, tl, seed, math_mode, mode=0):
+    from oracle import c_oracle as O
+    EnvSpec, RocketBatch = _engine()
+    spec = EnvSpec(dof, max_episode_steps=tl, reward_mode=mode, **cfg)
+    p = O.make_params(dof, max_episode_steps=tl, reward_mode=mode, **cfg)
+    env = RocketBatch(spec, N, seed=seed, math_mode=math_mode, debug_outputs=True)
+    vec = O.VecOracle(p, N, seed=seed)
+    return spec, env, vec
+
+
+def _compare_with_oracle(tag, spec, env, out, state_tol=G.STATE_TOL):
+    norm = spec.state_normalizer[:, None]
+    assert np.array_equal(env.done.cpu().numpy(), out["done"]), f"{tag}: done flags differ"
+    assert np.array_equal(env.truncated.cpu().numpy(), out["truncated"]), f"{tag}: truncated flags differ"
+    assert np.array_equal(env.natt.cpu().numpy(), out["natt"]), f"{tag}: RK45 attempt counts differ"
+    dev = np.abs(env.y_pre_reset.cpu().numpy() - out["y_pre_reset"]) / norm
+    assert dev.max() <= state_tol, f"{tag}: state deviates {dev.max():.3e}"
+    r = env.reward64.cpu().numpy()
+    assert (np.abs(r - out["reward"]) <= G.REWARD_TOL * np.maximum(1, np.abs(out["reward"]))).all(), f"{tag}: reward deviates"
+    assert np.abs(env.obs.cpu().numpy().astype(float) - out["obs"]).max() <= G.OBS_TOL, f"{tag}: obs deviates"
+    return float(dev.max())
+
+
+@pytest.mark.parametrize("math_mode", ["exact", "fast"])
+def test_config3_6dof_65536_teacher_forced(math_mode):
+    """BASELINE config 3 at full size: 65 536 envs, Philox ICs, random actions; every env compared with the oracle for 3 steps."""
+    N = 65536
+    spec, env, vec = _oracle_pair(6, G.cfg6(), N, 800, 2024, math_mode)
+    assert np.array_equal(env.reset().cpu().numpy(), vec.reset())        # reset is pure f32/f64 IEEE arithmetic: bit-exact
+    rng = np.random.RandomState(5)
+    worst = 0.0
+    for t in range(3):
+        a = rng.uniform(-1, 1, (N, 3)).astype(np.float32)
+        env.step_tensor(torch.as_tensor(a).cuda())
+        out = vec.step(a)
+        worst = max(worst, _compare_with_oracle(f"cfg3 step {t}", spec, env, out))
+        # teacher forcing: continue both sides from the oracle's state so that every step is a fresh one-step comparison
+        env.y.copy_(torch.as_tensor(vec.y).cuda())
+    print(f"config 3 one-step [{math_mode}] worst normalised deviation {worst:.3e}")
+
+
+@pytest.mark.parametrize("math_mode", ["exact", "fast"])
+def test_config3_6dof_subset_500_steps(math_mode):
+    """Free-running parity (auto-reset included) on 2048 envs x 500 steps of config 3."""
+    N, T = 2048, 500
+    spec, env, vec = _oracle_pair(6, G.cfg6(), N, 800, 99, math_mode)
+    env.reset(); vec.reset()
+    rng = np.random.RandomState(6)
+    worst, episodes = 0.0, 0
+    for t in range(T):
+        a = rng.uniform(-1, 1, (N, 3)).astype(np.float32)
+        env.step_tensor(torch.as_tensor(a).cuda())
+        out = vec.step(a)
+        worst = max(worst, _compare_with_oracle(f"cfg3 free t={t}", spec, env, out))
+        episodes += int(out["done"].sum())
+    assert episodes > N            # every env finished several episodes
+    st = env.read_stats()
+    assert st["steps"] == N * T and st["done"] == episodes
+    print(f"config 3 free-running [{math_mode}] worst {worst:.3e}, {episodes} episodes")
+
+
+@pytest.mark.parametrize("math_mode", ["exact", "fast"])
+def test_config2_3dof_4096_500_steps(math_mode):
+    """BASELINE config 2: 3DOF planar env (main.py config), 4096 envs, 500 random-action steps."""
+    N, T = 4096, 500
+    spec, env, vec = _oracle_pair(3, G.cfg3(), N, 3000, 7, math_mode)
+    env.reset(); vec.reset()
+    rng = np.random.RandomState(8)
+    worst, episodes = 0.0, 0
+    for t in range(T):
+        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        env.step_tensor(torch.as_tensor(a).cuda())
+        out = vec.step(a)
+        worst = max(worst, _compare_with_oracle(f"cfg2 t={t}", spec, env, out))
+        episodes += int(out["done"].sum())
+    assert episodes > 0
+    print(f"config 2 [{math_mode}] worst {worst:.3e}, {episodes} episodes")
+
+
+def test_rollout_kernel_equals_stepwise():
+    """The fused T-step rollout launch is bit-identical to T single-step launches."""
+    EnvSpec, RocketBatch = _engine()
+    N, T = 4096, 200
+    spec = EnvSpec(6, max_episode_steps=800, **G.cfg6())
+    a = torch.rand((T, N, 3), device="cuda") * 2 - 1
+    e1 = RocketBatch(spec, N, seed=3)
+    e2 = RocketBatch(spec, N, seed=3)
+    e1.reset(); e2.reset()
+    obs_buf = torch.zeros((T, N, 14), device="cuda")
+    rew_buf = torch.zeros((T, N), device="cuda")
+    done_buf = torch.zeros((T, N), dtype=torch.uint8, device="cuda")
+    e2.rollout(a, obs_buf, rew_buf, done_buf)
+    for t in range(T):
+        obs, rew, done = e1.step_tensor(a[t])
+        assert torch.equal(obs, obs_buf[t]) and torch.equal(rew, rew_buf[t]) and torch.equal(done, done_buf[t])
+    assert torch.equal(e1.y, e2.y) and torch.equal(e1.k, e2.k) and torch.equal(e1.episode, e2.episode)
+    assert e1.read_stats() == e2.read_stats()
+
+
+def test_sharding_is_invariant():
+    """Trajectories are keyed by the GLOBAL env index: two half-size shards reproduce the full batch bit for bit."""
+    EnvSpec, RocketBatch = _engine()
+    N, T = 2048, 150
+    spec = EnvSpec(6, max_episode_steps=800, **G.cfg6())
+    a = torch.rand((T, N, 3), device="cuda") * 2 - 1
+    full = RocketBatch(spec, N, seed=11)
+    lo = RocketBatch(spec, N // 2, seed=11, env_offset=0)
+    hi = RocketBatch(spec, N // 2, seed=11, env_offset=N // 2)
+    for e in (full, lo, hi):
+        e.reset()
+    for t in range(T):
+        full.step_tensor(a[t]); lo.step_tensor(a[t, : N // 2].contiguous()); hi.step_tensor(a[t, N // 2:].contiguous())
+    assert torch.equal(full.y[:, : N // 2], lo.y) and torch.equal(full.y[:, N // 2:], hi.y)
+    assert torch.equal(full.obs[N // 2:], hi.obs)
+    s, a_, b = full.read_stats(), lo.read_stats(), hi.read_stats()
+    assert all(s[k] == a_[k] + b[k] for k in ("steps", "attempts", "done", "landed", "viol", "trunc", "len_sum"))
+
+
+def test_full_size_invariants():
+    """Size-independent properties at 65 536 envs x 100 steps: unit quaternions, nfev in {8,14,20,...}, finite obs, counters."""
+    EnvSpec, RocketBatch = _engine()
+    N, T = 65536, 100
+    spec = EnvSpec(6, max_episode_steps=800, **G.cfg6())
+    env = RocketBatch(spec, N, seed=1, debug_outputs=True)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    steps = torch.zeros(N, dtype=torch.int64, device="cuda")
+    for t in range(T):
+        a = torch.rand((N, 3), device="cuda", generator=g) * 2 - 1
+        obs, rew, done = env.step_tensor(a)
+        q = env.y[6:10]
+        assert (q.pow(2).sum(0).sqrt() - 1).abs().max().item() < 1e-6        # f32-normalised ICs right after a reset
+        assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+        assert int(env.natt.min()) >= 1
+        steps += 1
+        # k counts steps since the last reset
+        assert torch.equal(env.k.long() * (1 - done.long()), steps * (1 - done.long()))
+        steps = steps * (1 - done.long())
+    st = env.read_stats()
+    assert st["steps"] == N * T and st["done"] > 0 and st["attempts"] >= st["steps"]
+    assert st["len_sum"] > 0 and st["viol"] + st["trunc"] <= st["done"]
+
+
+def test_empty_and_ragged_sizes():
+    EnvSpec, RocketBatch = _engine()
+    spec = EnvSpec(6, max_episode_steps=800, **G.cfg6())
+    for n in (1, 31, 33, 129):
+        env = RocketBatch(spec, n, seed=2)
+        ref = RocketBatch(spec, 256, seed=2)
+        env.reset(); ref.reset()
+        a = torch.rand((256, 3), device="cuda") * 2 - 1
+        for _ in range(5):
+            env.step_tensor(a[:n].contiguous()); ref.step_tensor(a)
+        assert torch.equal(env.y, ref.y[:, :n])
+    env0 = RocketBatch(spec, 0, seed=2)
+    env0.reset()
+    env0.step_tensor(torch.zeros((0, 3), device="cuda"))
