@@ -128,7 +128,10 @@ def run_ours(args):
         env.step_tensor(chunk[t])
     actions = torch.empty((W + K, n, 3), device=dev)
     actions.uniform_(-1, 1, generator=gen)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev) if args.l2_flush else None
+    # L2 flush between timed steps: READ a 256 MiB buffer (clean lines; a write-flush would leave 126 MB of dirty lines whose
+    # write-back lands inside the next timed kernel)
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev) if args.l2_flush else None
+    flush_sink = torch.zeros(1, dtype=torch.float32, device=dev)
     stat_gather = torch.zeros((world, 8), dtype=torch.int64, device=dev) if world > 1 else None
 
     def barrier():
@@ -149,7 +152,7 @@ def run_ours(args):
     t_wall0 = time.perf_counter()
     for t in range(K):
         if flush is not None:
-            flush.zero_()                    # evict L2 between timed iterations (outside the event pair)
+            torch.sum(flush, dim=(0,), keepdim=True, out=flush_sink)          # evict L2 between timed iterations (outside the event pair)
         ev[t][0].record()
         env.step_tensor(actions[W + t])
         ev[t][1].record()
@@ -189,6 +192,7 @@ def run_ours(args):
         e1.synchronize()
         b2b = n * K / (e0.elapsed_time(e1) * 1e-3)
         Tr = min(K, 200)
+        env.rollout(actions[W:W + 3])            # first launch of the rollout kernel (module load) outside the timing
         e0.record()
         env.rollout(actions[W:W + Tr])
         e1.record()
@@ -241,7 +245,7 @@ def run_ours(args):
                 "config": {"workload": "BASELINE config 3: 6DOF env_config (configuration_file.py:4-34), %d envs per GPU, random U(-1,1) "
                            "f32 actions, TimeLimit 800, auto-reset, one rlr_step launch per step" % n, "envs_per_gpu": n,
                            "total_envs": n * world, "math_mode": args.math,
-                           "l2": "256 MiB flush between timed steps" if args.l2_flush else "no flush",
+                           "l2": "256 MiB read-flush between timed steps (outside the event pairs)" if args.l2_flush else "no flush",
                            "state_prep": f"{PREP_STEPS} untimed random-action steps so episodes are desynchronised",
                            "collective": "all_gather of the 64-byte episode-statistics record per rank (NCCL), timed" if world > 1 else None},
                 "clocks": clocks, "e2e": e2e_d, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

@@ -64,12 +64,14 @@ typedef struct RlrParams {
     int32_t dt_ms;               /* timestep in whole milliseconds: t_k = k*dt_ms/1000 (simulator.py:245 rounds t to 3 decimals) */
     double  dt;
     double  normalizer[RLR_NMAX];
+    double  inv_normalizer[RLR_NMAX];              /* 1 / normalizer, used by RLR_MATH_FAST for the observation */
     float   ic_low[RLR_NMAX], ic_high[RLR_NMAX];   /* init_space Box (rocket_env.py:564-567 / :57-60) */
     float   pos_low[3], pos_high[3];               /* 6DOF position_bounds_space (rocket_env.py:615-620) */
     double  x_left, x_right, y_up;                 /* 3DOF bounds (rocket_env.py:97-100) */
     double  alfa, beta, eta, gamma, delta, kappa, xi;
     double  waypoint, landing_radius, maximum_velocity;
     double  att_traj_limit[3], att_land_limit[3], omega_lim[3];
+    double  att_traj_c[3], att_land_c[3];          /* cos(limit) for the two atan2 angles, sin(limit) for the asin angle (RLR_MATH_FAST) */
     double  max_gimbal;
     float   max_thrust;
     int32_t n_discrete;

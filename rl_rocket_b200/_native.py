@@ -15,14 +15,14 @@ ACT_NORMALIZED, ACT_PHYSICAL, ACT_DISCRETE = 0, 1, 2
 MATH_EXACT, MATH_FAST = 0, 1
 F64, F32 = 0, 1
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_C", "librlrocket.so")
+LIB_PATH = os.environ.get("RLR_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_C", "librlrocket.so")   # RLR_LIB: tuning builds only
 
 
 class RlrParams(C.Structure):
     _fields_ = [
         ("dof", C.c_int32), ("reward_mode", C.c_int32), ("max_episode_steps", C.c_int32), ("dt_ms", C.c_int32),
         ("dt", C.c_double),
-        ("normalizer", C.c_double * NMAX),
+        ("normalizer", C.c_double * NMAX), ("inv_normalizer", C.c_double * NMAX),
         ("ic_low", C.c_float * NMAX), ("ic_high", C.c_float * NMAX),
         ("pos_low", C.c_float * 3), ("pos_high", C.c_float * 3),
         ("x_left", C.c_double), ("x_right", C.c_double), ("y_up", C.c_double),
@@ -30,6 +30,7 @@ class RlrParams(C.Structure):
         ("delta", C.c_double), ("kappa", C.c_double), ("xi", C.c_double),
         ("waypoint", C.c_double), ("landing_radius", C.c_double), ("maximum_velocity", C.c_double),
         ("att_traj_limit", C.c_double * 3), ("att_land_limit", C.c_double * 3), ("omega_lim", C.c_double * 3),
+        ("att_traj_c", C.c_double * 3), ("att_land_c", C.c_double * 3),
         ("max_gimbal", C.c_double), ("max_thrust", C.c_float),
         ("n_discrete", C.c_int32), ("discrete_table", C.c_float * (2 * MAX_DISCRETE)),
     ]

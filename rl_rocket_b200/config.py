@@ -41,6 +41,20 @@ def timestep_ms(timestep):
     return int(ms)
 
 
+def _angle_limit_codes(limits):
+    """Limits on |euler_zyx| as the fast kernels test them without atan2/asin: for the two atan2 angles (index 0, 2)
+    |angle| > L  <=>  a < cos(L) * hypot(a, b);  for the asin angle (index 1)  |angle| > L  <=>  |v| > sin(L).
+    Limits outside the angle's range get sentinels that make the comparison constant."""
+    out = []
+    for i, L in enumerate(limits):
+        L = float(L)
+        if i == 1:
+            out.append(-1.0 if L < 0 else (2.0 if L >= np.pi / 2 else float(np.sin(L))))
+        else:
+            out.append(2.0 if L < 0 else (-2.0 if L >= np.pi else float(np.cos(L))))
+    return out
+
+
 class EnvSpec:
     """Everything derived from the constructor kwargs: the kernel POD plus the host-side arrays."""
 
@@ -133,6 +147,7 @@ class EnvSpec:
         rc = self.reward_coeff
         for i in range(NMAX):
             p.normalizer[i] = float(self.state_normalizer[i]) if i < self.ndim else 1.0
+            p.inv_normalizer[i] = 1.0 / p.normalizer[i]
         for i in range(self.ndim):
             p.ic_low[i] = float(self.ic_low[i])
             p.ic_high[i] = float(self.ic_high[i])
@@ -144,6 +159,8 @@ class EnvSpec:
             p.att_traj_limit[:] = [float(v) for v in tl["attitude_limit"]]
             p.att_land_limit[:] = [float(v) for v in lp["landing_attitude_limit"]]
             p.omega_lim[:] = [0.2, 0.2, 0.2]       # rocket_env.py:656: landing_params["omega_lim"] is ignored by the reference
+            p.att_traj_c[:] = _angle_limit_codes(p.att_traj_limit)
+            p.att_land_c[:] = _angle_limit_codes(p.att_land_limit)
         else:
             p.x_left, p.x_right, p.y_up = float(self.x_bound_left), float(self.x_bound_right), float(self.y_bound_up)
             p.waypoint, p.landing_radius = rc["waypoint"], rc["landing_radius"]

@@ -12,10 +12,12 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 OUT_DIR = os.path.join(os.path.dirname(HERE), "_C")
-OUT = os.path.join(OUT_DIR, "librlrocket.so")
+_V = os.environ.get("RLR_VARIANT", "A")
+OUT = os.path.join(OUT_DIR, "librlrocket.so" if _V == "A" else f"librlrocket_{_V}.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", HERE]
+VARIANT = {"A": [], "B": ["-DRLR_REGS6=96"], "C": ["-DRLR_REGS6=160"]}[os.environ.get("RLR_VARIANT", "A")]     # tuning builds
+COMMON = VARIANT + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", HERE]
 UNITS = [("kernels_exact.cu", ["-fmad=false"]), ("kernels_fast.cu", ["-fmad=true"]), ("fma_peak.cu", []), ("abi.cu", [])]
 
 
@@ -30,7 +32,7 @@ def build(force=False, verbose=False):
     objs = []
     procs = []
     for src, extra in UNITS:
-        obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(OUT_DIR, src.replace(".cu", f".{_V}.o"))
         cmd = [NVCC, *ARCH, *COMMON, *extra, "-c", os.path.join(HERE, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")

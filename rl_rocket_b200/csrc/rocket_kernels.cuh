@@ -20,6 +20,13 @@
 
 #include "rl_rocket_b200.h"
 
+#ifndef RLR_REGS6
+#define RLR_REGS6 128        // registers are granted per warp in units of 1024, i.e. 96 / 128 / 160 per thread: 128 lets 7 blocks
+                             // x 64 threads (shared memory: 7 x 31 KB) be resident = 448 threads/SM, which holds all 65 536
+                             // envs of BASELINE config 3 in ONE wave on 148 SMs (144 registers would drop to 6 blocks/SM)
+#endif
+// register cap of the step / rollout kernels: S::MAX_REGS registers per thread (see Sys6 / Sys3)
+#define RLR_KERNEL_BOUNDS(S) __maxnreg__(S::MAX_REGS)
 #ifndef RLR_NS
 #error "define RLR_NS before including rocket_kernels.cuh"
 #endif
@@ -69,6 +76,59 @@ RLR_DEV double min_step_at(double t) { return 10 * fabs(__longlong_as_double(__d
 RLR_DEV double py_max(double a, double b) { return (b > a) ? b : a; }
 RLR_DEV double py_min(double a, double b) { return (b < a) ? b : a; }
 
+// ------------------------------------------------------------------ division / sqrt / pow primitives
+// EXACT: IEEE division, sqrt and libdevice pow, i.e. the operations numpy / scipy perform.
+// FAST : branch-free hardware seed (MUFU.RCP64H / MUFU.RSQ64H, or an f32 exp2/log2 seed for the fifth root) refined by
+//        two Newton steps to ~1 ulp.  No slow-path calls: an IEEE `a / b` costs ~25 SASS instructions with a divergent
+//        call, 157 such sites made the first kernel 139 KB and instruction-cache bound (profiles/r01a_generic_kernel.md).
+#if RLR_EXACT
+RLR_DEV double rcp_(double x) { return 1.0 / x; }
+RLR_DEV double sqrt_(double x) { return sqrt(x); }
+RLR_DEV double rsqrt_(double x) { return 1.0 / sqrt(x); }
+RLR_DEV double pow_m02(double x) { return pow(x, -0.2); }
+RLR_DEV double pow_p02(double x) { return pow(x, 1.0 / 5.0); }
+#define RLR_DIV(a, b) ((a) / (b))
+#else
+RLR_DEV double rcp_(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    return r;
+}
+RLR_DEV double rsqrt_(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x * r, r, 1.0);
+    r = fma(0.5 * r, e, r);
+    e = fma(-x * r, r, 1.0);
+    r = fma(0.5 * r, e, r);
+    return r;
+}
+RLR_DEV double sqrt_(double x) { return (x == 0.0) ? 0.0 : x * rsqrt_(x); }      // NaN propagates
+// x^(-1/5): f32 seed (rel. err ~1e-6), Newton y <- y*(1.2 - 0.2*x*y^5) twice (error 3e^2 per step).  Out-of-range
+// or non-finite x yields garbage/NaN that the callers' max(0.2, .) / min(10, .) clamps resolve like the exact path.
+RLR_DEV double pow_m02(double x) {
+    const float xf = fminf(fmaxf((float)x, 1e-30f), 1e30f);
+    double y = (double)__powf(xf, -0.2f);
+    const double mx = -0.2 * x;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double y2 = y * y;
+        const double y5 = (y2 * y2) * y;
+        y = y * fma(mx, y5, 1.2);
+    }
+    return y;
+}
+RLR_DEV double pow_p02(double x) {          // x^(1/5) = x * (x^(-1/5))^4
+    const double y = pow_m02(x), y2 = y * y;
+    return x * (y2 * y2);
+}
+#define RLR_DIV(a, b) ((a) * rcp_(b))
+#endif
+
 // ------------------------------------------------------------------ Dormand-Prince tableau
 #define A10 (1.0 / 5)
 #define A20 (3.0 / 40)
@@ -109,7 +169,7 @@ __constant__ double c_P[7][4] = {
 // ------------------------------------------------------------------ dynamical systems
 // 6DOF: y = [r(3), v(3), q0..q3, w(3), m]   (simulator.py:259-378)
 struct Sys6 {
-    static constexpr int N = 14, EV = 0, NA = 3, NOBS = 14;
+    static constexpr int N = 14, EV = 0, NA = 3, NOBS = 14, MAX_REGS = RLR_REGS6;
     struct Ctx { double Tb0, Tb1, Tb2, tau1, tau2, dm; };
 
     RLR_DEV static void make_ctx(Ctx& c, const float* u) {
@@ -168,7 +228,7 @@ struct Sys6 {
 
 // 3DOF: y = [x, z, theta, vx, vz, omega, m]   (simulator.py:88-130)
 struct Sys3 {
-    static constexpr int N = 7, EV = 1, NA = 2, NOBS = 7;
+    static constexpr int N = 7, EV = 1, NA = 2, NOBS = 7, MAX_REGS = 168;
     struct Ctx { double delta, T, torque, dm; };
 
     RLR_DEV static void make_ctx(Ctx& c, const float* u) {
@@ -190,8 +250,8 @@ struct Sys3 {
         // NB: drag multiplies cos(phi) on BOTH axes -- reference behaviour (simulator.py:122-123)
         const double Acp = A * cp;
         d[0] = vx; d[1] = vz; d[2] = y[5];
-        d[3] = ((c.T * cdp - 0.0) - Acp) / mass;
-        d[4] = ((c.T * sdp + 0.0) - Acp) / mass - 9.81;
+        d[3] = RLR_DIV((c.T * cdp - 0.0) - Acp, mass);
+        d[4] = RLR_DIV((c.T * sdp + 0.0) - Acp, mass) - 9.81;
         d[5] = (-0.0 - c.torque) / 6.04e6;
         d[6] = c.dm;
     }
@@ -202,8 +262,8 @@ template <int N>
 RLR_DEV double rms_ratio(const double (&a)[N], const double (&s)[N]) {
     double acc = 0.0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) { double q = a[i] / s[i]; acc += q * q; }
-    return sqrt(acc) / sqrt((double)N);
+    for (int i = 0; i < N; ++i) { double q = RLR_DIV(a[i], s[i]); acc += q * q; }
+    return RLR_DIV(sqrt_(acc), sqrt((double)N));
 }
 
 // dense-output polynomial row for component i: Q_i[c] = sum_j K[j][i] * P[j][c]
@@ -280,17 +340,17 @@ RLR_DEV int rk45_solve(const typename S::Ctx& c, double t0, double t_bound, doub
         for (int i = 0; i < N; ++i) scale[i] = atol + fabs(y[i]) * rtol;
         const double d0 = rms_ratio<N>(y, scale);
         const double d1 = rms_ratio<N>(K[0], scale);
-        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : RLR_DIV(0.01 * d0, d1);
         h0 = py_min(h0, interval);
 #pragma unroll
         for (int i = 0; i < N; ++i) y1[i] = y[i] + h0 * K[0][i];
         S::rhs(c, y1, f1);
 #pragma unroll
         for (int i = 0; i < N; ++i) f1[i] = f1[i] - K[0][i];
-        const double d2 = rms_ratio<N>(f1, scale) / h0;
+        const double d2 = RLR_DIV(rms_ratio<N>(f1, scale), h0);
         double h1;
         if (d1 <= 1e-15 && d2 <= 1e-15) h1 = py_max(1e-6, h0 * 1e-3);
-        else h1 = pow(0.01 / py_max(d1, d2), 1.0 / 5.0);
+        else h1 = pow_p02(RLR_DIV(0.01, py_max(d1, d2)));
         h_abs = py_min(py_min(100 * h0, h1), interval);
     }
     double t = t0;
@@ -333,12 +393,12 @@ RLR_DEV int rk45_solve(const typename S::Ctx& c, double t0, double t_bound, doub
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const double sc = atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol;
-            const double e = ((((((K[0][i] * E0 + K[2][i] * E2) + K[3][i] * E3) + K[4][i] * E4) + K[5][i] * E5) + K[6][i] * E6) * h) / sc;
+            const double e = RLR_DIV((((((K[0][i] * E0 + K[2][i] * E2) + K[3][i] * E3) + K[4][i] * E4) + K[5][i] * E5) + K[6][i] * E6) * h, sc);
             acc += e * e;
         }
-        const double err = sqrt(acc) / sqrt((double)N);
+        const double err = RLR_DIV(sqrt_(acc), sqrt((double)N));
         if (err < 1) {
-            double factor = (err == 0) ? 10.0 : py_min(10.0, 0.9 * pow(err, -0.2));
+            double factor = (err == 0) ? 10.0 : py_min(10.0, 0.9 * pow_m02(err));
             if (rejected) factor = py_min(1.0, factor);
             h_abs *= factor;
             // ---- terminal event g(y) = y[EV]  (ivp.py:134-158, 678-699)
@@ -367,6 +427,291 @@ RLR_DEV int rk45_solve(const typename S::Ctx& c, double t0, double t_bound, doub
             rejected = true;
         }
     }
+    return status;
+}
+
+
+// ------------------------------------------------------------------ 6DOF: shared-memory stage matrix, rolled stage loop
+// Row s (1..6) of c_RKA: coefficients a_sj, j = 0..5; row 6 is B (y_new is "stage 6": FSAL).
+__constant__ double c_RKA[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {A10, 0, 0, 0, 0, 0},
+    {A20, A21, 0, 0, 0, 0},
+    {A30, A31, A32, 0, 0, 0},
+    {A40, A41, A42, A43, 0, 0},
+    {A50, A51, A52, A53, A54, 0},
+    {B0, 0, B2, B3, B4, B5}};
+__constant__ double c_RKB[6] = {B0, 0, B2, B3, B4, B5};
+__constant__ double c_RKE[7] = {E0, 0, E2, E3, E4, E5, E6};
+
+// Right-hand side restricted to the components that need arithmetic: d = [dv(3), dq(4), dw(3)].
+// dr is the stage velocity itself and dm is constant over the env step (simulator.py:280, :291-292).
+RLR_DEV void rhs6r(const Sys6::Ctx& c, const double (&q)[4], const double (&wv)[3], double m, double (&d)[10]) {
+    const double q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
+    const double wx = wv[0], wy = wv[1], wz = wv[2];
+    const double n2 = q1 * q1 + q2 * q2 + q3 * q3 + q0 * q0;
+#if RLR_EXACT
+    const double nq = sqrt(n2);
+    const double x = q1 / nq, yy = q2 / nq, z = q3 / nq, w = q0 / nq;
+#else
+    const double rn = rsqrt_(n2);
+    const double x = q1 * rn, yy = q2 * rn, z = q3 * rn, w = q0 * rn;
+#endif
+    const double inv_m = rcp_(m);
+    const double x2 = x * x, y2 = yy * yy, z2 = z * z, w2 = w * w;
+    const double xy = x * yy, zw = z * w, xz = x * z, yw = yy * w, yz = yy * z, xw = x * w;
+    const double R00 = x2 - y2 - z2 + w2, R01 = 2 * (xy - zw), R02 = 2 * (xz + yw);
+    const double R10 = 2 * (xy + zw), R11 = -x2 + y2 - z2 + w2, R12 = 2 * (yz - xw);
+    const double R20 = 2 * (xz - yw), R21 = 2 * (yz + xw), R22 = -x2 - y2 + z2 + w2;
+    const double F0 = R00 * c.Tb0 + R01 * c.Tb1 + R02 * c.Tb2;
+    const double F1 = R10 * c.Tb0 + R11 * c.Tb1 + R12 * c.Tb2;
+    const double F2 = R20 * c.Tb0 + R21 * c.Tb1 + R22 * c.Tb2;
+    d[0] = inv_m * F0 + (-9.81);
+    d[1] = inv_m * F1;
+    d[2] = inv_m * F2;
+    d[3] = 0.5 * (((-wx) * q1 + (-wy) * q2) + (-wz) * q3);
+    d[4] = 0.5 * ((wx * q0 + wz * q2) + (-wy) * q3);
+    d[5] = 0.5 * ((wy * q0 + (-wz) * q1) + wx * q3);
+    d[6] = 0.5 * ((wz * q0 + wy * q1) + (-wx) * q2);
+    const double J0 = 75350.25, J1 = 6037675.13, J2 = 6037675.13;
+    const double Jw0 = J0 * wx, Jw1 = J1 * wy, Jw2 = J2 * wz;
+    const double c0 = wy * Jw2 - wz * Jw1, c1 = wz * Jw0 - wx * Jw2, c2 = wx * Jw1 - wy * Jw0;
+    d[7] = (1.0 / J0) * (0.0 - c0);
+    d[8] = (1.0 / J1) * (c.tau1 - c1);
+    d[9] = (1.0 / J2) * (c.tau2 - c2);
+}
+
+// Rare path (once per landing): dense output + Brent root + final state, on a full [7][14] stage matrix in local memory.
+// Per component the three non-trivial polynomial coefficients are accumulated as independent FMA chains (P[.][0] is
+// (1,0,...,0) and P[1][.] is 0, so those terms are exact no-ops and are skipped).
+__device__ __noinline__ void event_finish14(const double* Kf, const double* y_old, double t_old, double h, double t_new, int ev, double* y_out) {
+    double root = 0.0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        const int lo = (pass == 0) ? ev : 0, hi = (pass == 0) ? ev + 1 : 14;
+#pragma unroll 1
+        for (int i = lo; i < hi; ++i) {
+            const double k0 = Kf[i], k2 = Kf[2 * 14 + i], k3 = Kf[3 * 14 + i], k4 = Kf[4 * 14 + i], k5 = Kf[5 * 14 + i], k6 = Kf[6 * 14 + i];
+            double Q[4];
+            Q[0] = k0;
+#pragma unroll
+            for (int cc = 1; cc < 4; ++cc)
+                Q[cc] = ((((k0 * c_P[0][cc] + k2 * c_P[2][cc]) + k3 * c_P[3][cc]) + k4 * c_P[4][cc]) + k5 * c_P[5][cc]) + k6 * c_P[6][cc];
+            if (pass == 0) root = brentq_event(Q[0], Q[1], Q[2], Q[3], y_old[i], t_old, h, t_old, t_new);
+            else y_out[i] = dense_at(Q, y_old[i], t_old, h, root);
+        }
+    }
+}
+
+// solve_ivp for the 6DOF system.  y = [r(3), v(3), q(4), w(3), m] in registers; the stage derivatives K0..K5 (10 doubles
+// each: dv, dq, dw -- dr is the stage velocity, dm a per-step constant) live in shared memory at
+// sK[(stage*10 + c) * BS6 + tid]: consecutive threads -> consecutive 8-byte words (conflict-free), a fixed stride between
+// stages so that the stage loop walks one pointer.  K0 is f(y) (FSAL), K6 = f(y_new) stays in registers until accepted.
+constexpr int BS6 = 64;                                   // threads per block of the 6DOF kernels (compile time: LDS offsets are immediates)
+constexpr int KROW = 10 * BS6;                            // doubles between consecutive stages
+constexpr size_t SMEM6_BYTES = 6 * KROW * sizeof(double); // 30 KB per block
+
+RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&y)[14], int& natt, double* __restrict__ sKt) {
+    // sKt = sK + tid
+    constexpr double rtol = 1e-3, atol = 1e-6;
+#define KS(j, cc) sKt[(j) * KROW + (cc) * BS6]
+    double kk[10];
+    {
+        const double q[4] = {y[6], y[7], y[8], y[9]};
+        const double wv[3] = {y[10], y[11], y[12]};
+        rhs6r(c, q, wv, y[13], kk);
+#pragma unroll
+        for (int cc = 0; cc < 10; ++cc) KS(0, cc) = kk[cc];
+    }
+    natt = 0;
+    // ---- select_initial_step (common.py:68-134) on the full 14-vector f0 = [v, dv, dq, dw, dm]
+    double h_abs;
+    {
+        const double interval = fabs(t_bound - t0);
+        double isc[14];
+#pragma unroll
+        for (int i = 0; i < 14; ++i) {
+            const double sc = atol + fabs(y[i]) * rtol;
+#if RLR_EXACT
+            isc[i] = sc;
+#else
+            isc[i] = rcp_(sc);
+#endif
+        }
+#if RLR_EXACT
+#define SCALED(a, i) ((a) / isc[i])
+#else
+#define SCALED(a, i) ((a) * isc[i])
+#endif
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 14; ++i) { const double u_ = SCALED(y[i], i); a0 += u_ * u_; }
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const double u_ = SCALED(y[3 + i], i); a1 += u_ * u_; }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) { const double u_ = SCALED(kk[i], 3 + i); a1 += u_ * u_; }
+        { const double u_ = SCALED(c.dm, 13); a1 += u_ * u_; }
+        const double rs14 = sqrt(14.0);
+        const double d0 = RLR_DIV(sqrt_(a0), rs14), d1 = RLR_DIV(sqrt_(a1), rs14);
+        double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : RLR_DIV(0.01 * d0, d1);
+        h0 = py_min(h0, interval);
+        double v1[3], q1[4], w1[3], f1[10];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) v1[i] = y[3 + i] + h0 * kk[i];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) q1[i] = y[6 + i] + h0 * kk[3 + i];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) w1[i] = y[10 + i] + h0 * kk[7 + i];
+        const double m1 = y[13] + h0 * c.dm;
+        rhs6r(c, q1, w1, m1, f1);
+        double a2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { const double u_ = SCALED(v1[i] - y[3 + i], i); a2 += u_ * u_; }
+#pragma unroll
+        for (int i = 0; i < 10; ++i) { const double u_ = SCALED(f1[i] - kk[i], 3 + i); a2 += u_ * u_; }
+        { const double u_ = SCALED(c.dm - c.dm, 13); a2 += u_ * u_; }
+        const double d2 = RLR_DIV(RLR_DIV(sqrt_(a2), rs14), h0);
+        double h1;
+        if (d1 <= 1e-15 && d2 <= 1e-15) h1 = py_max(1e-6, h0 * 1e-3);
+        else h1 = pow_p02(RLR_DIV(0.01, py_max(d1, d2)));
+        h_abs = py_min(py_min(100 * h0, h1), interval);
+#undef SCALED
+    }
+    double t = t0;
+    double min_step = min_step_at(t);
+    if (h_abs < min_step) h_abs = min_step;
+    bool rejected = false;
+    int status;
+#pragma unroll 1
+    for (;;) {
+        if (h_abs < min_step) { status = -1; break; }
+        double t_new = t + h_abs;
+        if (t_new - t_bound > 0) t_new = t_bound;
+        const double h = t_new - t;
+        h_abs = fabs(h);
+        ++natt;
+        double sv[3], sq[4], sw[3], sm = y[13], aB[3], aE[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { aB[i] = y[3 + i] * B0; aE[i] = y[3 + i] * E0; }
+        // ---- rk_step (rk.py:14-71); stage 6 is y_new (row 6 of c_RKA = B)
+#pragma unroll 1
+        for (int s = 1; s <= 6; ++s) {
+            double acc[10];
+            double a = c_RKA[s][0];
+#pragma unroll
+            for (int cc = 0; cc < 10; ++cc) acc[cc] = KS(0, cc) * a;
+            double accm = c.dm * a;
+            const double* kp = sKt + KROW;
+#pragma unroll 1
+            for (int j = 1; j < s; ++j, kp += KROW) {
+                a = c_RKA[s][j];
+#pragma unroll
+                for (int cc = 0; cc < 10; ++cc) acc[cc] += kp[cc * BS6] * a;
+                accm += c.dm * a;
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sv[i] = y[3 + i] + acc[i] * h;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sq[i] = y[6 + i] + acc[3 + i] * h;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sw[i] = y[10 + i] + acc[7 + i] * h;
+            sm = y[13] + accm * h;
+            if (s <= 5) {
+                const double bs = c_RKB[s], es = c_RKE[s];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { aB[i] += sv[i] * bs; aE[i] += sv[i] * es; }
+            }
+            rhs6r(c, sq, sw, sm, kk);
+            if (s <= 5) {
+                double* ko = sKt + s * KROW;
+#pragma unroll
+                for (int cc = 0; cc < 10; ++cc) ko[cc * BS6] = kk[cc];
+            }
+        }
+        // ---- error norm (rk.py:101-107): components in index order r, v, q, w, m
+        double rn[3];
+        double ssum = 0.0;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            rn[i] = y[i] + h * aB[i];
+            const double sc = atol + fmax(fabs(y[i]), fabs(rn[i])) * rtol;
+            const double e = RLR_DIV((aE[i] + sv[i] * E6) * h, sc);
+            ssum += e * e;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 10; ++cc) {
+            const double yo = y[3 + cc];
+            const double yn = (cc < 3) ? sv[cc] : ((cc < 7) ? sq[cc - 3] : sw[cc - 7]);
+            const double sc = atol + fmax(fabs(yo), fabs(yn)) * rtol;
+            const double es = ((((KS(0, cc) * E0 + KS(2, cc) * E2) + KS(3, cc) * E3) + KS(4, cc) * E4) + KS(5, cc) * E5) + kk[cc] * E6;
+            const double e = RLR_DIV(es * h, sc);
+            ssum += e * e;
+        }
+        {
+            const double dm = c.dm;
+            const double es = (((((dm * E0 + dm * 0.0) + dm * E2) + dm * E3) + dm * E4) + dm * E5) + dm * E6;
+            const double sc = atol + fmax(fabs(y[13]), fabs(sm)) * rtol;
+            const double e = RLR_DIV(es * h, sc);
+            ssum += e * e;
+        }
+        const double err = RLR_DIV(sqrt_(ssum), sqrt(14.0));
+        if (err < 1) {
+            double factor = (err == 0) ? 10.0 : py_min(10.0, 0.9 * pow_m02(err));
+            if (rejected) factor = py_min(1.0, factor);
+            h_abs *= factor;
+            const double g = y[0], g_new = rn[0];
+            if (((g <= 0) && (g_new >= 0)) || ((g >= 0) && (g_new <= 0))) {
+                // ---- terminal ground event: rebuild the full stage matrix in local memory (stage velocities recomputed)
+                double Kf[7 * 14], yo[14], yout[14];
+#pragma unroll
+                for (int i = 0; i < 14; ++i) yo[i] = y[i];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { Kf[i] = y[3 + i]; Kf[6 * 14 + i] = sv[i]; }
+#pragma unroll
+                for (int cc = 0; cc < 10; ++cc) Kf[6 * 14 + 3 + cc] = kk[cc];
+#pragma unroll 1
+                for (int s = 0; s <= 5; ++s) {
+                    if (s >= 1) {
+                        double a = c_RKA[s][0];
+                        double a3[3] = {KS(0, 0) * a, KS(0, 1) * a, KS(0, 2) * a};
+#pragma unroll 1
+                        for (int j = 1; j < s; ++j) {
+                            a = c_RKA[s][j];
+#pragma unroll
+                            for (int i = 0; i < 3; ++i) a3[i] += KS(j, i) * a;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 3; ++i) Kf[s * 14 + i] = y[3 + i] + a3[i] * h;
+                    }
+#pragma unroll 1
+                    for (int cc = 0; cc < 10; ++cc) Kf[s * 14 + 3 + cc] = KS(s, cc);
+                }
+#pragma unroll 1
+                for (int s = 0; s <= 6; ++s) Kf[s * 14 + 13] = c.dm;
+                event_finish14(Kf, yo, t, h, t_new, 0, yout);
+#pragma unroll
+                for (int i = 0; i < 14; ++i) y[i] = yout[i];
+                status = 1;
+                break;
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { y[i] = rn[i]; y[3 + i] = sv[i]; y[10 + i] = sw[i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) y[6 + i] = sq[i];
+            y[13] = sm;
+#pragma unroll
+            for (int cc = 0; cc < 10; ++cc) KS(0, cc) = kk[cc];     // FSAL: f(y_new) becomes K0
+            t = t_new;
+            if (t - t_bound >= 0) { status = 0; break; }
+            rejected = false;
+            min_step = min_step_at(t);
+            if (h_abs < min_step) h_abs = min_step;
+        } else {
+            h_abs *= py_max(0.2, 0.9 * pow_m02(err));
+            rejected = true;
+        }
+    }
+#undef KS
     return status;
 }
 
@@ -435,26 +780,47 @@ RLR_DEV void reward6(const RlrParams& p, const float (&s)[14], const float* u, f
         vh0 = (double)s[3] - (-1.0); tau = 100.0;
     }
     const double vh1 = (double)s[4], vh2 = (double)s[5];
-    const double nr = sqrt((rh0 * rh0 + rh1 * rh1) + rh2 * rh2);
-    const double nv = sqrt((vh0 * vh0 + vh1 * vh1) + vh2 * vh2);
-    const double t_go = nr / nv;
+    const double nr = sqrt_((rh0 * rh0 + rh1 * rh1) + rh2 * rh2);
+    const double nv = sqrt_((vh0 * vh0 + vh1 * vh1) + vh2 * vh2);
+    const double t_go = RLR_DIV(nr, nv);
     const double den = py_max(1e-3, nr);
-    const double fac = 1 - exp(-t_go / tau);
+    const double fac = 1 - exp(RLR_DIV(-t_go, tau));
     const double mv0 = (double)(-v0);
+#if RLR_EXACT
     const double d0 = (double)s[3] - (mv0 * (rh0 / den)) * fac;
     const double d1 = (double)s[4] - (mv0 * (rh1 / den)) * fac;
     const double d2 = (double)s[5] - (mv0 * (rh2 / den)) * fac;
+#else
+    const double iden = rcp_(den);
+    const double d0 = (double)s[3] - (mv0 * (rh0 * iden)) * fac;
+    const double d1 = (double)s[4] - (mv0 * (rh1 * iden)) * fac;
+    const double d2 = (double)s[5] - (mv0 * (rh2 * iden)) * fac;
+#endif
     // Rotation.from_quat(roll(q_f32,-1)).as_euler("zyx")
     const double q0 = s[6], q1 = s[7], q2 = s[8], q3 = s[9];
+#if RLR_EXACT
     const double nq = sqrt(((q1 * q1 + q2 * q2) + q3 * q3) + q0 * q0);
     const double x = q1 / nq, yy = q2 / nq, z = q3 / nq, w = q0 / nq;
+#else
+    const double rnq = rsqrt_(((q1 * q1 + q2 * q2) + q3 * q3) + q0 * q0);
+    const double x = q1 * rnq, yy = q2 * rnq, z = q3 * rnq, w = q0 * rnq;
+#endif
     const double R00 = x * x - yy * yy - z * z + w * w, R01 = 2 * (x * yy - z * w), R02 = 2 * (x * z + yy * w);
     const double R12 = 2 * (yy * z - x * w), R22 = -x * x - yy * yy + z * z + w * w;
+#if RLR_EXACT
     const double ang0 = atan2(-R01, R00);
     const double ang1 = asin(fmin(1.0, fmax(-1.0, R02)));
     const double ang2 = atan2(-R12, R22);
     const int att_viol = (fabs(ang0) > p.att_traj_limit[0]) | (fabs(ang1) > p.att_traj_limit[1]) | (fabs(ang2) > p.att_traj_limit[2]);
     const int att_ok = (fabs(ang0) < p.att_land_limit[0]) | (fabs(ang1) < p.att_land_limit[1]) | (fabs(ang2) < p.att_land_limit[2]);
+#else
+    // The Euler angles are only compared with limits: |atan2(b, a)| > L  <=>  a < cos(L) * hypot(a, b)  (cos is decreasing on
+    // [0, pi]) and |asin(v)| > L  <=>  |v| > sin(L); cos(L) / sin(L) come precomputed from the host (with sentinels for limits
+    // outside [0, pi] resp. [0, pi/2]), so no atan2 / asin is evaluated.
+    const double hy0 = sqrt_(R00 * R00 + R01 * R01), hy2 = sqrt_(R22 * R22 + R12 * R12), av1 = fabs(R02);
+    const int att_viol = (R00 < p.att_traj_c[0] * hy0) | (av1 > p.att_traj_c[1]) | (R22 < p.att_traj_c[2] * hy2);
+    const int att_ok = (R00 > p.att_land_c[0] * hy0) | (av1 < p.att_land_c[1]) | (R22 > p.att_land_c[2] * hy2);
+#endif
     const int om_ok = ((double)fabsf(s[10]) < p.omega_lim[0]) | ((double)fabsf(s[11]) < p.omega_lim[1]) | ((double)fabsf(s[12]) < p.omega_lim[2]);
     const float rn = f32_norm3(s[0], s[1], s[2]), vn = f32_norm3(s[3], s[4], s[5]);
     const int landed = (s[0] <= 1e-3f) && ((double)vn < p.maximum_velocity) && ((double)rn < p.landing_radius) && att_ok && om_ok;
@@ -462,7 +828,7 @@ RLR_DEV void reward6(const RlrParams& p, const float (&s)[14], const float* u, f
 #pragma unroll
     for (int i = 0; i < 3; ++i) inside = inside && (s[i] >= p.pos_low[i]) && (s[i] <= p.pos_high[i]);
     const int viol = !inside;
-    o.terms[0] = p.alfa * sqrt((d0 * d0 + d1 * d1) + d2 * d2);
+    o.terms[0] = p.alfa * sqrt_((d0 * d0 + d1 * d1) + d2 * d2);
     o.terms[1] = (double)fmul((float)p.beta, u[2]);
     o.terms[2] = p.eta;
     o.terms[3] = p.gamma * (double)att_viol;
@@ -568,19 +934,31 @@ struct StepFlags { int done, trunc, viol, landed, status, natt; };
 // Integrate one env step, compute reward/obs/flags.  `st` is updated to the post-step state
 // (NOT reset).  obs = observation of the post-step state.
 template <class S>
-RLR_DEV void env_step(const RlrParams& p, EnvState<S>& st, const float (&u)[3], float a_thr, float (&obs)[S::N], StepRes& res, StepFlags& fl) {
+RLR_DEV void env_step(const RlrParams& p, EnvState<S>& st, const float (&u)[3], float a_thr, float (&obs)[S::N], StepRes& res, StepFlags& fl,
+                      double* sK) {
     typename S::Ctx c;
     S::make_ctx(c, u);
     const double t = (double)((long long)st.k * (long long)p.dt_ms) / 1000.0;   // round(t + dt, 3)  (simulator.py:245)
     int natt;
-    const int status = rk45_solve<S>(c, t, t + p.dt, st.y, natt);
+    int status;
+    if constexpr (S::N == 14) status = rk45_solve6(c, t, t + p.dt, st.y, natt, sK + threadIdx.x);
+    else status = rk45_solve<S>(c, t, t + p.dt, st.y, natt);
     float s[S::N];
     if constexpr (S::N == 14) {
-        const double nq = sqrt(((st.y[6] * st.y[6] + st.y[7] * st.y[7]) + st.y[8] * st.y[8]) + st.y[9] * st.y[9]);
+        const double n2 = ((st.y[6] * st.y[6] + st.y[7] * st.y[7]) + st.y[8] * st.y[8]) + st.y[9] * st.y[9];
+#if RLR_EXACT
+        const double nq = sqrt(n2);
 #pragma unroll
         for (int i = 6; i < 10; ++i) st.y[i] = st.y[i] / nq;        // simulator.py:250
 #pragma unroll
         for (int i = 0; i < S::N; ++i) { s[i] = (float)st.y[i]; obs[i] = (float)(st.y[i] / p.normalizer[i]); }   // rocket_env.py:695, :963-964
+#else
+        const double rnq = rsqrt_(n2);
+#pragma unroll
+        for (int i = 6; i < 10; ++i) st.y[i] = st.y[i] * rnq;
+#pragma unroll
+        for (int i = 0; i < S::N; ++i) { s[i] = (float)st.y[i]; obs[i] = (float)(st.y[i] * p.inv_normalizer[i]); }
+#endif
         reward6(p, (const float(&)[14])s, u, a_thr, st.v0, status, res);
     } else {
         const double pi2 = 2.0 * 3.141592653589793;
@@ -622,25 +1000,39 @@ RLR_DEV void write_obs(const RlrParams& p, float* dst, int64_t i, const float (&
     }
 }
 
-// warp-shuffle reduction of the episode statistics, one atomic per warp and slot
+// warp-shuffle reduction of the episode statistics: counters packed into one 64-bit word (5 x 6-bit counts of <= 32 lanes
+// + attempts in the upper bits), lengths and fixed-point returns in two more; lane 0 issues one atomic per non-zero slot.
+RLR_DEV unsigned long long warp_sum(unsigned long long x) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
+    return x;
+}
 RLR_DEV void accumulate_stats(unsigned long long* stats, bool active, const StepFlags& fl, int ep_len, double ep_ret) {
     if (stats == nullptr) return;
-    unsigned long long v[RLR_NSTATS];
-    v[RLR_STAT_STEPS] = active ? 1ull : 0ull;
-    v[RLR_STAT_ATTEMPTS] = active ? (unsigned long long)fl.natt : 0ull;
     const bool fin = active && fl.done;
-    v[RLR_STAT_DONE] = fin ? 1ull : 0ull;
-    v[RLR_STAT_LANDED] = (fin && fl.landed) ? 1ull : 0ull;
-    v[RLR_STAT_VIOL] = (fin && fl.viol) ? 1ull : 0ull;
-    v[RLR_STAT_TRUNC] = (fin && fl.trunc) ? 1ull : 0ull;
-    v[RLR_STAT_LEN_SUM] = fin ? (unsigned long long)ep_len : 0ull;
-    v[RLR_STAT_RET_SUM] = fin ? (unsigned long long)(long long)llrint(ep_ret * 1048576.0) : 0ull;
-#pragma unroll
-    for (int s = 0; s < RLR_NSTATS; ++s) {
-        unsigned long long x = v[s];
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
-        if ((threadIdx.x & 31) == 0 && x != 0ull) atomicAdd(stats + s, x);
+    unsigned long long packed = (active ? 1ull : 0ull) | ((fin ? 1ull : 0ull) << 6) | (((fin && fl.landed) ? 1ull : 0ull) << 12) |
+                                (((fin && fl.viol) ? 1ull : 0ull) << 18) | (((fin && fl.trunc) ? 1ull : 0ull) << 24) |
+                                ((active ? (unsigned long long)fl.natt : 0ull) << 30);
+    packed = warp_sum(packed);
+    const unsigned any_fin = __ballot_sync(0xffffffffu, fin);
+    unsigned long long len = 0ull, ret = 0ull;
+    if (any_fin) {       // warp-uniform
+        len = warp_sum(fin ? (unsigned long long)ep_len : 0ull);
+        ret = warp_sum(fin ? (unsigned long long)(long long)llrint(ep_ret * 1048576.0) : 0ull);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        const unsigned long long n_steps = packed & 63ull, n_done = (packed >> 6) & 63ull, n_land = (packed >> 12) & 63ull;
+        const unsigned long long n_viol = (packed >> 18) & 63ull, n_trunc = (packed >> 24) & 63ull, n_att = packed >> 30;
+        if (n_steps) atomicAdd(stats + RLR_STAT_STEPS, n_steps);
+        if (n_att) atomicAdd(stats + RLR_STAT_ATTEMPTS, n_att);
+        if (n_done) {
+            atomicAdd(stats + RLR_STAT_DONE, n_done);
+            if (n_land) atomicAdd(stats + RLR_STAT_LANDED, n_land);
+            if (n_viol) atomicAdd(stats + RLR_STAT_VIOL, n_viol);
+            if (n_trunc) atomicAdd(stats + RLR_STAT_TRUNC, n_trunc);
+            atomicAdd(stats + RLR_STAT_LEN_SUM, len);
+            atomicAdd(stats + RLR_STAT_RET_SUM, ret);
+        }
     }
 }
 
@@ -662,8 +1054,9 @@ RLR_DEV void finish_and_reset(const RlrParams& p, EnvState<S>& st, const float* 
 }
 
 template <class S>
-__global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ RlrParams p, RlrState gs, const void* actions, int action_kind,
+__global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrParams p, RlrState gs, const void* actions, int action_kind,
                                                    const float* ic_inject, RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed) {
+    extern __shared__ double sK[];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n;
     StepFlags fl = {0, 0, 0, 0, 0, 0};
@@ -676,7 +1069,7 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ RlrPa
         map_action<S>(p, actions, action_kind, i, u, a_thr);
         float obs[S::N];
         StepRes res;
-        env_step<S>(p, st, u, a_thr, obs, res, fl);
+        env_step<S>(p, st, u, a_thr, obs, res, fl, sK);
         ep_len = st.k; ep_ret = st.ep_ret;
         if (out.reward) out.reward[i] = (float)res.reward;
         if (out.reward64) out.reward64[i] = res.reward;
@@ -728,9 +1121,10 @@ __global__ void __launch_bounds__(128) reset_kernel(const __grid_constant__ RlrP
 
 // T fused steps: state stays in registers between env steps; per-step outputs go to [T][n][..] rollout buffers
 template <class S>
-__global__ void __launch_bounds__(128) rollout_kernel(const __grid_constant__ RlrParams p, RlrState gs, const void* actions, int action_kind, int T,
+__global__ void RLR_KERNEL_BOUNDS(S) rollout_kernel(const __grid_constant__ RlrParams p, RlrState gs, const void* actions, int action_kind, int T,
                                                       float* obs_buf, float* reward_buf, uint8_t* done_buf, uint8_t* trunc_buf, float* last_obs,
                                                       unsigned long long* stats, int64_t n, int64_t env_offset, uint64_t seed) {
+    extern __shared__ double sK[];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n;
     EnvState<S> st;
@@ -749,7 +1143,7 @@ __global__ void __launch_bounds__(128) rollout_kernel(const __grid_constant__ Rl
             float u[3], a_thr;
             map_action<S>(p, a_t, action_kind, i, u, a_thr);
             StepRes res;
-            env_step<S>(p, st, u, a_thr, obs, res, fl);
+            env_step<S>(p, st, u, a_thr, obs, res, fl, sK);
             ep_len = st.k; ep_ret = st.ep_ret;
             if (fl.done) finish_and_reset<S>(p, st, nullptr, i, env_offset, seed, obs);
             if (obs_buf) write_obs<S>(p, obs_buf + (int64_t)t * n * no, i, obs);
@@ -766,13 +1160,65 @@ __global__ void __launch_bounds__(128) rollout_kernel(const __grid_constant__ Rl
 }
 
 // ------------------------------------------------------------------ host launchers (called from abi.cu)
+// Launch geometry.  6DOF: 64-thread blocks, 30 KB of dynamic shared memory each (stage matrix).  The number of co-resident
+// blocks per SM comes from the occupancy calculator; when the grid would end in a nearly empty last wave, residency is
+// reduced (by padding the dynamic shared-memory request) to the value that maximises  utilisation * sqrt(resident blocks)
+// -- e.g. 65 536 envs on 148 SMs: 7 blocks/SM -> 1024 blocks on 1036 slots, one wave.
+struct Geometry { int block; size_t smem; int blocks_per_sm; };
+struct GeometryEntry { const void* kern; int64_t n; Geometry g; };
+
+template <typename Kern>
+Geometry pick_geometry(Kern kern, int64_t n, int block, size_t smem_min) {
+    static int sm_count = 0, smem_per_sm = 0;
+    static GeometryEntry cache[8] = {};
+    static int cache_next = 0;
+    const void* key = (const void*)kern;
+    for (int e = 0; e < 8; ++e)
+        if (cache[e].kern == key && cache[e].n == n) return cache[e].g;
+    if (sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        if (sm_count <= 0) sm_count = 148;
+        if (smem_per_sm <= 0) smem_per_sm = 233472;
+    }
+    Geometry best = {block, smem_min, 1};
+    int nb_max = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_max, kern, block, smem_min) != cudaSuccess || nb_max <= 0) nb_max = 1;
+    best.blocks_per_sm = nb_max;
+    if (smem_min > 0) {
+        double best_score = -1.0;
+        for (int nb = nb_max; nb >= (nb_max + 1) / 2; --nb) {
+            const double cap = (double)sm_count * nb * block;
+            const double util = (double)n / (ceil((double)n / cap) * cap);
+            const double score = util * sqrt((double)nb);
+            if (score > best_score * 1.001) { best_score = score; best.blocks_per_sm = nb; }
+        }
+        if (best.blocks_per_sm < nb_max) {
+            // pad the request so that exactly blocks_per_sm blocks fit (1 KB per block is reserved by the driver)
+            size_t padded = ((size_t)smem_per_sm / best.blocks_per_sm - 1024) & ~(size_t)1023;
+            if (padded > 227 * 1024) padded = 227 * 1024;
+            if (padded > smem_min) best.smem = padded;
+        }
+        if (best.smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem);
+    }
+    cudaGetLastError();
+    cache[cache_next] = {key, n, best};
+    cache_next = (cache_next + 1) % 8;
+    return best;
+}
+
 inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
 int launch_step(const RlrParams* p, RlrState st, const void* actions, int action_kind, const float* ic_inject, RlrStepOut out, int64_t n,
                 int64_t env_offset, uint64_t seed, cudaStream_t stream) {
-    const int block = 128;
-    if (p->dof == 6) step_kernel<Sys6><<<grid_for(n, block), block, 0, stream>>>(*p, st, actions, action_kind, ic_inject, out, n, env_offset, seed);
-    else step_kernel<Sys3><<<grid_for(n, block), block, 0, stream>>>(*p, st, actions, action_kind, ic_inject, out, n, env_offset, seed);
+    if (p->dof == 6) {
+        const Geometry g = pick_geometry(step_kernel<Sys6>, n, BS6, SMEM6_BYTES);
+        step_kernel<Sys6><<<grid_for(n, g.block), g.block, g.smem, stream>>>(*p, st, actions, action_kind, ic_inject, out, n, env_offset, seed);
+    } else {
+        step_kernel<Sys3><<<grid_for(n, 128), 128, 0, stream>>>(*p, st, actions, action_kind, ic_inject, out, n, env_offset, seed);
+    }
     return (int)cudaGetLastError();
 }
 
@@ -787,13 +1233,14 @@ int launch_reset(const RlrParams* p, RlrState st, const uint8_t* mask, const flo
 int launch_rollout(const RlrParams* p, RlrState st, const void* actions, int action_kind, int T, float* obs_buf, float* reward_buf,
                    uint8_t* done_buf, uint8_t* trunc_buf, float* last_obs, unsigned long long* stats, int64_t n, int64_t env_offset,
                    uint64_t seed, cudaStream_t stream) {
-    const int block = 128;
-    if (p->dof == 6)
-        rollout_kernel<Sys6><<<grid_for(n, block), block, 0, stream>>>(*p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf, trunc_buf,
-                                                                       last_obs, stats, n, env_offset, seed);
-    else
-        rollout_kernel<Sys3><<<grid_for(n, block), block, 0, stream>>>(*p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf, trunc_buf,
-                                                                       last_obs, stats, n, env_offset, seed);
+    if (p->dof == 6) {
+        const Geometry g = pick_geometry(rollout_kernel<Sys6>, n, BS6, SMEM6_BYTES);
+        rollout_kernel<Sys6><<<grid_for(n, g.block), g.block, g.smem, stream>>>(*p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf,
+                                                                              trunc_buf, last_obs, stats, n, env_offset, seed);
+    } else {
+        rollout_kernel<Sys3><<<grid_for(n, 128), 128, 0, stream>>>(*p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf, trunc_buf,
+                                                                   last_obs, stats, n, env_offset, seed);
+    }
     return (int)cudaGetLastError();
 }
 

@@ -21,7 +21,7 @@ class RocketBatch:
         self.lib = N.load()                      # raises if the CUDA extension is not built
         if not torch.cuda.is_available():
             raise RuntimeError("rl_rocket_b200 needs a CUDA device (there is no CPU fallback)")
-        self.spec = spec
+        self.spec = spec                         # (property: also caches the byref of the params POD)
         self.n = int(num_envs)
         self.device = torch.device(device)
         self.seed = int(spec.seed if seed is None else seed)
@@ -50,18 +50,33 @@ class RocketBatch:
         self.y_pre_reset = torch.zeros((nd, n), dtype=torch.float64, device=dev) if self.debug else None
         self.reward_terms = torch.zeros((6, n), dtype=torch.float64, device=dev) if self.debug else None
         self.launches = 0
+        # the buffers above are persistent, so the pointer structs handed to the C ABI are built once
+        self._st = N.RlrState(_ptr(self.y), _ptr(self.k), _ptr(self.episode), _ptr(self.v0), _ptr(self.ep_ret))
+        self._ot = N.RlrStepOut(_ptr(self.obs), _ptr(self.reward), _ptr(self.reward64), _ptr(self.done), _ptr(self.truncated),
+                                _ptr(self.terminal_obs), _ptr(self.fin_ret), _ptr(self.fin_len), _ptr(self.flags), _ptr(self.natt),
+                                _ptr(self.y_pre_reset), _ptr(self.reward_terms), _ptr(self.stats))
+        self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self._act_shape = (n, spec.nact)
+        self._step_fn = self.lib.rlr_step
 
     # -- raw structs -------------------------------------------------------------------------
+    @property
+    def spec(self):
+        return self._spec
+
+    @spec.setter
+    def spec(self, value):
+        self._spec = value
+        self._params_ref = C.byref(value.params)
+
     def _state(self):
-        return N.RlrState(_ptr(self.y), _ptr(self.k), _ptr(self.episode), _ptr(self.v0), _ptr(self.ep_ret))
+        return self._st
 
     def _out(self):
-        return N.RlrStepOut(_ptr(self.obs), _ptr(self.reward), _ptr(self.reward64), _ptr(self.done), _ptr(self.truncated),
-                            _ptr(self.terminal_obs), _ptr(self.fin_ret), _ptr(self.fin_len), _ptr(self.flags), _ptr(self.natt),
-                            _ptr(self.y_pre_reset), _ptr(self.reward_terms), _ptr(self.stats))
+        return self._ot
 
     def _stream(self):
-        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        return torch.cuda.current_stream(self._dev_index).cuda_stream
 
     def _check_actions(self, actions, leading=()):
         spec = self.spec
@@ -88,7 +103,7 @@ class RocketBatch:
                 assert tuple(ic.shape) == (self.n, self.spec.ndim)
             if mask is not None:
                 mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
-            N.check(self.lib.rlr_reset(C.byref(self.spec.params), N.F64, self._state(), _ptr(mask), _ptr(ic), _ptr(self.obs),
+            N.check(self.lib.rlr_reset(self._params_ref, N.F64, self._state(), _ptr(mask), _ptr(ic), _ptr(self.obs),
                                        self.n, self.env_offset, self.seed, self._stream()))
             self.launches += 1
         return self.obs
@@ -96,13 +111,25 @@ class RocketBatch:
     def step_tensor(self, actions, physical=False, ic_inject=None):
         """One step for all envs.  actions: cuda f32 [n, nact] (or i64 [n] discrete).  Returns (obs, reward, done) device tensors
         (views of persistent buffers, overwritten by the next call)."""
+        if (actions.dtype is torch.float32 and tuple(actions.shape) == self._act_shape and actions.is_contiguous()
+                and actions.device == self.device and ic_inject is None):
+            # hot path: no per-call allocation, one ctypes call
+            if torch.cuda.current_device() != self._dev_index:
+                torch.cuda.set_device(self._dev_index)
+            rc = self._step_fn(self._params_ref, N.F64, self.math_mode, self._st, actions.data_ptr(),
+                               N.ACT_PHYSICAL if physical else N.ACT_NORMALIZED, None, self._ot, self.n, self.env_offset, self.seed,
+                               torch.cuda.current_stream(self._dev_index).cuda_stream)
+            if rc:
+                N.check(rc)
+            self.launches += 1
+            return self.obs, self.reward, self.done
         actions, kind = self._check_actions(actions)
         if kind is None:
             kind = N.ACT_PHYSICAL if physical else N.ACT_NORMALIZED
         with torch.cuda.device(self.device):
             if ic_inject is not None:
                 ic_inject = torch.as_tensor(ic_inject, dtype=torch.float32, device=self.device).contiguous()
-            N.check(self.lib.rlr_step(C.byref(self.spec.params), N.F64, self.math_mode, self._state(), _ptr(actions), kind,
+            N.check(self.lib.rlr_step(self._params_ref, N.F64, self.math_mode, self._state(), _ptr(actions), kind,
                                       _ptr(ic_inject), self._out(), self.n, self.env_offset, self.seed, self._stream()))
             self.launches += 1
         return self.obs, self.reward, self.done
@@ -114,7 +141,7 @@ class RocketBatch:
         if kind is None:
             kind = N.ACT_PHYSICAL if physical else N.ACT_NORMALIZED
         with torch.cuda.device(self.device):
-            N.check(self.lib.rlr_rollout(C.byref(self.spec.params), N.F64, self.math_mode, self._state(), _ptr(actions), kind, T,
+            N.check(self.lib.rlr_rollout(self._params_ref, N.F64, self.math_mode, self._state(), _ptr(actions), kind, T,
                                          _ptr(obs_buf), _ptr(reward_buf), _ptr(done_buf), _ptr(trunc_buf), _ptr(self.obs),
                                          _ptr(self.stats), self.n, self.env_offset, self.seed, self._stream()))
             self.launches += 1

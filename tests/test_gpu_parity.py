@@ -130,13 +130,14 @@ def test_config2_3dof_4096_500_steps(math_mode):
 
 
 def test_rollout_kernel_equals_stepwise():
-    """The fused T-step rollout launch is bit-identical to T single-step launches."""
+    """The fused T-step rollout launch is bit-identical to T single-step launches (exact math: the two kernels execute the
+    same IEEE operation sequence; in fast mode the compiler may contract FMAs differently in the two kernels)."""
     EnvSpec, RocketBatch = _engine()
     N, T = 4096, 200
     spec = EnvSpec(6, max_episode_steps=800, **G.cfg6())
     a = torch.rand((T, N, 3), device="cuda") * 2 - 1
-    e1 = RocketBatch(spec, N, seed=3)
-    e2 = RocketBatch(spec, N, seed=3)
+    e1 = RocketBatch(spec, N, seed=3, math_mode="exact")
+    e2 = RocketBatch(spec, N, seed=3, math_mode="exact")
     e1.reset(); e2.reset()
     obs_buf = torch.zeros((T, N, 14), device="cuda")
     rew_buf = torch.zeros((T, N), device="cuda")
@@ -147,6 +148,26 @@ def test_rollout_kernel_equals_stepwise():
         assert torch.equal(obs, obs_buf[t]) and torch.equal(rew, rew_buf[t]) and torch.equal(done, done_buf[t])
     assert torch.equal(e1.y, e2.y) and torch.equal(e1.k, e2.k) and torch.equal(e1.episode, e2.episode)
     assert e1.read_stats() == e2.read_stats()
+
+
+def test_rollout_kernel_fast_matches_stepwise_within_tolerance():
+    EnvSpec, RocketBatch = _engine()
+    N, T = 4096, 200
+    spec = EnvSpec(6, max_episode_steps=800, **G.cfg6())
+    a = torch.rand((T, N, 3), device="cuda") * 2 - 1
+    e1 = RocketBatch(spec, N, seed=3, math_mode="fast")
+    e2 = RocketBatch(spec, N, seed=3, math_mode="fast")
+    e1.reset(); e2.reset()
+    done_buf = torch.zeros((T, N), dtype=torch.uint8, device="cuda")
+    rew_buf = torch.zeros((T, N), device="cuda")
+    e2.rollout(a, None, rew_buf, done_buf)
+    for t in range(T):
+        obs, rew, done = e1.step_tensor(a[t])
+        assert torch.equal(done, done_buf[t])
+        assert (rew - rew_buf[t]).abs().max().item() <= 1e-5
+    norm = torch.as_tensor(spec.state_normalizer, device="cuda")[:, None]
+    assert ((e1.y - e2.y).abs() / norm).max().item() <= G.STATE_TOL
+    assert torch.equal(e1.k, e2.k) and torch.equal(e1.episode, e2.episode)
 
 
 def test_sharding_is_invariant():
