@@ -481,36 +481,53 @@ RLR_DEV void rhs6r(const Sys6::Ctx& c, const double (&q)[4], const double (&wv)[
     d[9] = (1.0 / J2) * (c.tau2 - c2);
 }
 
-// Rare path (once per landing): dense output + Brent root + final state, on a full [7][14] stage matrix in local memory.
-// Per component the three non-trivial polynomial coefficients are accumulated as independent FMA chains (P[.][0] is
-// (1,0,...,0) and P[1][.] is 0, so those terms are exact no-ops and are skipped).
-__device__ __noinline__ void event_finish14(const double* Kf, const double* y_old, double t_old, double h, double t_new, int ev, double* y_out) {
-    double root = 0.0;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; ++pass) {
-        const int lo = (pass == 0) ? ev : 0, hi = (pass == 0) ? ev + 1 : 14;
-#pragma unroll 1
-        for (int i = lo; i < hi; ++i) {
-            const double k0 = Kf[i], k2 = Kf[2 * 14 + i], k3 = Kf[3 * 14 + i], k4 = Kf[4 * 14 + i], k5 = Kf[5 * 14 + i], k6 = Kf[6 * 14 + i];
-            double Q[4];
-            Q[0] = k0;
+constexpr int BS6 = 64;                                   // threads per block of the 6DOF kernels (compile time: LDS offsets are immediates)
+constexpr int KROW = 10 * BS6;                            // doubles between consecutive stages
+constexpr size_t SMEM6_BYTES = 6 * KROW * sizeof(double); // 30 KB per block
+
+// Terminal ground event of the 6DOF solve (ivp.py:678-699): dense output Q = K^T P (rk.py:554-565, :715-737), Brent root on the
+// height polynomial, final state y(t_e).  buf = [y(14) | K6(10) | v_new(3) | dm, t_old, h, t_new]; y(t_e) is written to buf[0..13].
+// K0..K5 come from shared memory.  P[.][0] = (1,0,..,0) and P[1][.] = 0 make those terms exact no-ops, so every component needs
+// three independent 6-term FMA chains; the position rows of K are the stage velocities, recomputed from the dv rows.
+__device__ __noinline__ void event_path6(const double* __restrict__ sKt, double* __restrict__ buf) {
+#define KS(j, cc) sKt[(j) * KROW + (cc) * BS6]
+    const double dm = buf[27], t = buf[28], h = buf[29], t_new = buf[30];
+    double vs[5][3];                       // stage velocities 2..5 (K_1 has zero weight in P)
 #pragma unroll
-            for (int cc = 1; cc < 4; ++cc)
-                Q[cc] = ((((k0 * c_P[0][cc] + k2 * c_P[2][cc]) + k3 * c_P[3][cc]) + k4 * c_P[4][cc]) + k5 * c_P[5][cc]) + k6 * c_P[6][cc];
-            if (pass == 0) root = brentq_event(Q[0], Q[1], Q[2], Q[3], y_old[i], t_old, h, t_old, t_new);
-            else y_out[i] = dense_at(Q, y_old[i], t_old, h, root);
+    for (int s = 2; s <= 5; ++s) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double a3 = KS(0, i) * c_RKA[s][0];
+#pragma unroll
+            for (int j = 1; j < s; ++j) a3 += KS(j, i) * c_RKA[s][j];
+            vs[s - 1][i] = buf[3 + i] + a3 * h;
         }
     }
+#define DENSE_Q(k0, k2, k3, k4, k5, k6, cc) \
+    ((((((k0) * c_P[0][cc] + (k2) * c_P[2][cc]) + (k3) * c_P[3][cc]) + (k4) * c_P[4][cc]) + (k5) * c_P[5][cc]) + (k6) * c_P[6][cc])
+    const double vx0 = buf[3], vx6 = buf[24];
+    const double root = brentq_event(vx0, DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 1),
+                                     DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 2),
+                                     DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 3), buf[0], t, h, t, t_new);
+    const double xx = RLR_DIV(root - t, h);
+    const double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
+#define DENSE_Y(yold, k0, k2, k3, k4, k5, k6)                                                                \
+    (h * ((((k0) * p1 + DENSE_Q(k0, k2, k3, k4, k5, k6, 1) * p2) + DENSE_Q(k0, k2, k3, k4, k5, k6, 2) * p3) + \
+          DENSE_Q(k0, k2, k3, k4, k5, k6, 3) * p4) + (yold))
+#pragma unroll
+    for (int i = 0; i < 3; ++i) buf[i] = DENSE_Y(buf[i], buf[3 + i], vs[1][i], vs[2][i], vs[3][i], vs[4][i], buf[24 + i]);   // uses the OLD v
+#pragma unroll
+    for (int cc = 0; cc < 10; ++cc) buf[3 + cc] = DENSE_Y(buf[3 + cc], KS(0, cc), KS(2, cc), KS(3, cc), KS(4, cc), KS(5, cc), buf[14 + cc]);
+    buf[13] = DENSE_Y(buf[13], dm, dm, dm, dm, dm, dm);
+#undef DENSE_Y
+#undef DENSE_Q
+#undef KS
 }
 
 // solve_ivp for the 6DOF system.  y = [r(3), v(3), q(4), w(3), m] in registers; the stage derivatives K0..K5 (10 doubles
 // each: dv, dq, dw -- dr is the stage velocity, dm a per-step constant) live in shared memory at
 // sK[(stage*10 + c) * BS6 + tid]: consecutive threads -> consecutive 8-byte words (conflict-free), a fixed stride between
 // stages so that the stage loop walks one pointer.  K0 is f(y) (FSAL), K6 = f(y_new) stays in registers until accepted.
-constexpr int BS6 = 64;                                   // threads per block of the 6DOF kernels (compile time: LDS offsets are immediates)
-constexpr int KROW = 10 * BS6;                            // doubles between consecutive stages
-constexpr size_t SMEM6_BYTES = 6 * KROW * sizeof(double); // 30 KB per block
-
 RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&y)[14], int& natt, double* __restrict__ sKt) {
     // sKt = sK + tid
     constexpr double rtol = 1e-3, atol = 1e-6;
@@ -661,36 +678,18 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
             h_abs *= factor;
             const double g = y[0], g_new = rn[0];
             if (((g <= 0) && (g_new >= 0)) || ((g >= 0) && (g_new <= 0))) {
-                // ---- terminal ground event: rebuild the full stage matrix in local memory (stage velocities recomputed)
-                double Kf[7 * 14], yo[14], yout[14];
+                // ---- terminal ground event: rare (once per landing) -> out-of-line, arguments through a small local buffer
+                double ebuf[32];
 #pragma unroll
-                for (int i = 0; i < 14; ++i) yo[i] = y[i];
+                for (int i = 0; i < 14; ++i) ebuf[i] = y[i];
 #pragma unroll
-                for (int i = 0; i < 3; ++i) { Kf[i] = y[3 + i]; Kf[6 * 14 + i] = sv[i]; }
+                for (int cc = 0; cc < 10; ++cc) ebuf[14 + cc] = kk[cc];
 #pragma unroll
-                for (int cc = 0; cc < 10; ++cc) Kf[6 * 14 + 3 + cc] = kk[cc];
-#pragma unroll 1
-                for (int s = 0; s <= 5; ++s) {
-                    if (s >= 1) {
-                        double a = c_RKA[s][0];
-                        double a3[3] = {KS(0, 0) * a, KS(0, 1) * a, KS(0, 2) * a};
-#pragma unroll 1
-                        for (int j = 1; j < s; ++j) {
-                            a = c_RKA[s][j];
+                for (int i = 0; i < 3; ++i) ebuf[24 + i] = sv[i];
+                ebuf[27] = c.dm; ebuf[28] = t; ebuf[29] = h; ebuf[30] = t_new;
+                event_path6(sKt, ebuf);
 #pragma unroll
-                            for (int i = 0; i < 3; ++i) a3[i] += KS(j, i) * a;
-                        }
-#pragma unroll
-                        for (int i = 0; i < 3; ++i) Kf[s * 14 + i] = y[3 + i] + a3[i] * h;
-                    }
-#pragma unroll 1
-                    for (int cc = 0; cc < 10; ++cc) Kf[s * 14 + 3 + cc] = KS(s, cc);
-                }
-#pragma unroll 1
-                for (int s = 0; s <= 6; ++s) Kf[s * 14 + 13] = c.dm;
-                event_finish14(Kf, yo, t, h, t_new, 0, yout);
-#pragma unroll
-                for (int i = 0; i < 14; ++i) y[i] = yout[i];
+                for (int i = 0; i < 14; ++i) y[i] = ebuf[i];
                 status = 1;
                 break;
             }
@@ -729,8 +728,8 @@ RLR_DEV void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
 
 template <int N>
 RLR_DEV void sample_ic(const RlrParams& p, uint64_t seed, int64_t env, int32_t episode, float (&ic)[N]) {
-#pragma unroll
-    for (int b = 0; b * 2 < N; ++b) {
+#pragma unroll 1
+    for (int b = 0; b * 2 < N; ++b) {      // rolled: the reset path is rare per thread, keep its code small
         uint32_t c[4] = {(uint32_t)b, (uint32_t)episode, (uint32_t)((uint64_t)env & 0xffffffffu), (uint32_t)((uint64_t)env >> 32)};
         philox4x32_10(c, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
 #pragma unroll
@@ -758,7 +757,14 @@ RLR_DEV void reset_from_ic(const RlrParams& p, float (&ic)[S::N], double (&y)[S:
         v0 = f32_norm2(ic[3], ic[4]);
     }
 #pragma unroll
-    for (int i = 0; i < S::N; ++i) { y[i] = (double)ic[i]; obs[i] = (float)((double)ic[i] / p.normalizer[i]); }
+    for (int i = 0; i < S::N; ++i) {
+        y[i] = (double)ic[i];
+#if RLR_EXACT
+        obs[i] = (float)((double)ic[i] / p.normalizer[i]);
+#else
+        obs[i] = (float)((double)ic[i] * p.inv_normalizer[i]);
+#endif
+    }
 }
 
 // ------------------------------------------------------------------ reward / termination epilogues
