@@ -1,0 +1,175 @@
+"""GPU tests of the reference-facing surface: gym single-env facades, the SB3-style VecEnv (infos / auto-reset / Monitor stats),
+wrappers, and an SB3 `collect_rollouts`-shaped harness (BASELINE config 5).  Golden data = the live reference's own outputs."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+from tests import goldutil as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("tag", ["null", "nonnull", "mixed"])
+def test_rocket6dof_facade_replays_kat2(tag):
+    """test_6DOF_environment.py:12-34 scenario through the gym facade (list / ndarray actions, reward as float, info dict)."""
+    from rl_rocket_b200.envs import Rocket6DOF
+    g = G.load("kat_6dof.npz")
+    cfg = G.cfg6()
+    cfg["ICRange"] = [0] * 14
+    env = Rocket6DOF(**cfg)
+    assert env.observation_space.shape == (14,) and env.action_space.shape == (3,)
+    obs = env.reset()
+    assert obs.dtype == np.float32 and np.array_equal(obs, g[f"kat2_{tag}_obs"][0])
+    act = g[f"kat2_{tag}_action"]
+    act = act.tolist() if tag == "null" else act              # the reference script passes a python list
+    n, done, R = 0, False, 0.0
+    while not done:
+        obs, r, done, info = env.step(act)
+        assert isinstance(r, float) and isinstance(done, bool) and obs.dtype == np.float32
+        assert np.abs((env.state - g[f"kat2_{tag}_y"][n]) / env.state_normalizer).max() < 1e-12
+        assert abs(r - g[f"kat2_{tag}_reward"][n]) < 1e-11
+        assert done == bool(g[f"kat2_{tag}_done"][n]) and info["bounds_violation"] == bool(g[f"kat2_{tag}_viol"][n])
+        assert np.abs(obs.astype(float) - g[f"kat2_{tag}_obs"][n + 1]).max() < G.OBS_TOL
+        assert np.abs(np.array(list(info["rewards_dict"].values())) - g[f"kat2_{tag}_terms"][n]).max() < 1e-11
+        R += r
+        n += 1
+    assert n == len(g[f"kat2_{tag}_reward"]) and len(env.SIM.states) == n + 1
+    assert abs(R - g[f"kat2_{tag}_reward"].sum()) < 1e-9
+    assert env.used_mass() >= 0 and env.states_to_dataframe().shape == (n + 1, 14)
+
+
+def test_rocket3dof_facade_replays_kat3():
+    from rl_rocket_b200.envs import Rocket
+    g = G.load("kat_3dof.npz")
+    cfg = G.cfg3()
+    cfg["ICRange"] = [0] * 7
+    env = Rocket(**cfg)
+    obs = env.reset()
+    assert obs.dtype == np.float64 and np.abs(obs - g["kat3_mixed_obs"][0]).max() < 1e-15
+    n, done = 0, False
+    while not done:
+        obs, r, done, info = env.step(g["kat3_mixed_action"])
+        assert np.abs((env.y - g["kat3_mixed_y"][n]) / env.state_normalizer).max() < 1e-11
+        assert abs(r - g["kat3_mixed_reward"][n]) < 1e-10 and done == bool(g["kat3_mixed_done"][n])
+        assert np.abs(obs - g["kat3_mixed_obs"][n + 1]).max() < 1e-6
+        n += 1
+    assert n == 285
+
+
+def test_wrappers_on_the_facades():
+    from rl_rocket_b200.envs import Rocket, Rocket1DOF
+    from rl_rocket_b200 import wrappers as W
+    env = W.TimeLimit(W.DiscreteActions3DOF(Rocket(**G.cfg3())), max_episode_steps=5)
+    env.reset()
+    for k in range(5):
+        obs, r, done, info = env.step(2)
+    assert done and info["TimeLimit.truncated"] is True and obs.shape == (7,)
+    e1 = Rocket1DOF(timestep=0.05, reward_coeff=G.cfg3()["reward_coeff"])
+    o = e1.reset()
+    assert o.shape == (2,) and e1.action_space.shape == (1,)
+    o, r, d, info = e1.step(np.float32([0.3]))
+    assert o.shape == (2,) and abs(e1.y[0]) < 1e-6 and abs(e1.y[3]) < 1e-5        # gimbal 0: stays on the vertical (theta = f32(pi/2))
+    a = W.RewardAnnealing(Rocket(**G.cfg3()))
+    a.reset()
+    _, r, _, info = a.step(np.float32([0.1, -0.5]))
+    assert set(info["rewards_dict"]) == {"attitude_constraint", "rew_goal", "thrust_penalty"} and r == pytest.approx(-0.004 * 0.5)
+
+
+def test_vecenv_matches_golden_dummyvecenv_semantics():
+    """RocketVecEnv.step == DummyVecEnv([Monitor(TimeLimit(env))]).step on the golden trajectory: obs after auto-reset,
+    f32 rewards, dones, terminal_observation, TimeLimit.truncated and Monitor's episode r / l."""
+    from rl_rocket_b200.vec_env import RocketVecEnv
+    for name, tl in (("traj_6dof.npz", 800), ("traj_6dof_timelimit.npz", 25)):
+        g = G.load(name)
+        T, N = g["done"].shape
+        venv = RocketVecEnv(N, dof=6, max_episode_steps=tl, math_mode="exact", **G.cfg6())
+        venv.seed(int(g["seed"]))
+        obs = venv.reset()
+        assert obs.shape == (N, 14) and obs.dtype == np.float32 and np.abs(obs.astype(float) - g["obs0"]).max() <= G.OBS_TOL
+        ep_r, ep_l = np.zeros(N), np.zeros(N, int)
+        n_eps = 0
+        for t in range(T):
+            obs, rew, done, infos = venv.step(g["actions"][t])
+            assert rew.dtype == np.float32 and done.dtype == bool and len(infos) == N
+            assert np.array_equal(done, g["done"][t].astype(bool))
+            assert np.abs(obs.astype(float) - g["obs"][t]).max() <= G.OBS_TOL
+            assert np.abs(rew - g["reward"][t].astype(np.float32)).max() <= 1e-5
+            ep_r += g["reward"][t]
+            ep_l += 1
+            for i in range(N):
+                if done[i]:
+                    inf = infos[i]
+                    assert np.abs(inf["terminal_observation"].astype(float) - g["terminal_obs"][t, i]).max() <= G.OBS_TOL
+                    assert inf["TimeLimit.truncated"] == bool(g["truncated"][t, i])
+                    assert inf["episode"]["l"] == ep_l[i] and abs(inf["episode"]["r"] - ep_r[i]) < 1e-5
+                    assert inf["bounds_violation"] == bool(g["viol"][t, i])
+                    ep_r[i], ep_l[i] = 0.0, 0
+                    n_eps += 1
+                else:
+                    assert infos[i] == {}
+        st = venv.episode_stats()
+        assert st["done"] == n_eps == int(g["done"].sum()) and st["steps"] == T * N
+
+
+def test_vecenv_discrete_and_annealing_modes():
+    from rl_rocket_b200.vec_env import RocketVecEnv
+    g = G.load("traj_3dof_discrete.npz")
+    T, N = g["done"].shape
+    venv = RocketVecEnv(N, dof=3, max_episode_steps=3000, discrete_actions=True, math_mode="exact", **G.cfg3())
+    venv.seed(int(g["seed"]))
+    venv.reset()
+    assert venv.action_space.n == 4
+    for t in range(T):
+        obs, rew, done, infos = venv.step(g["actions"][t])
+        assert np.array_equal(done, g["done"][t].astype(bool)) and np.abs(rew - g["reward"][t].astype(np.float32)).max() <= 1e-4
+    g = G.load("traj_6dof_annealing.npz")
+    T, N = g["done"].shape
+    venv = RocketVecEnv(N, dof=6, max_episode_steps=800, math_mode="exact", **G.cfg6())
+    venv.set_reward_annealing(True)              # second training phase of main_6DOF.py:95-103
+    venv.seed(int(g["seed"]))
+    venv.reset()
+    for t in range(T):
+        obs, rew, done, infos = venv.step(g["actions"][t])
+        assert np.array_equal(done, g["done"][t].astype(bool)) and np.abs(rew - g["reward"][t].astype(np.float32)).max() <= 1e-6
+
+
+def test_config5_sb3_style_rollout_collection():
+    """BASELINE config 5: the calling pattern of SB3's OnPolicyAlgorithm.collect_rollouts (policy forward on the GPU, clip to
+    the Box, env.step, bootstrap on TimeLimit.truncated via terminal_observation, episode info buffer), on 6DOF with the
+    vtarg-shaped reward.  Checked against the oracle stepping the same actions."""
+    from oracle import c_oracle as O
+    from rl_rocket_b200.vec_env import RocketVecEnv
+    N, n_steps, tl = 256, 128, 40
+    cfg = G.cfg6()
+    venv = RocketVecEnv(N, dof=6, max_episode_steps=tl, math_mode="exact", **cfg)
+    venv.seed(77)
+    vec = O.VecOracle(O.make_params(6, max_episode_steps=tl, **cfg), N, seed=77)
+    torch.manual_seed(0)
+    policy = torch.nn.Sequential(torch.nn.Linear(14, 64), torch.nn.Tanh(), torch.nn.Linear(64, 64), torch.nn.Tanh(),
+                                 torch.nn.Linear(64, 3)).cuda()
+    value = torch.nn.Sequential(torch.nn.Linear(14, 64), torch.nn.Tanh(), torch.nn.Linear(64, 1)).cuda()
+    obs = venv.reset()
+    assert np.array_equal(obs, vec.reset())
+    buf_obs = np.zeros((n_steps, N, 14), np.float32)
+    buf_rew = np.zeros((n_steps, N), np.float32)
+    ep_info, n_boot = [], 0
+    for t in range(n_steps):
+        with torch.no_grad():
+            mean = policy(torch.as_tensor(obs).cuda())
+            actions = (mean + 0.3 * torch.randn_like(mean)).cpu().numpy()
+        clipped = np.clip(actions, venv.action_space.low, venv.action_space.high)
+        new_obs, rewards, dones, infos = venv.step(clipped)
+        out = vec.step(clipped.astype(np.float32))
+        assert np.array_equal(dones, out["done"].astype(bool)) and np.abs(new_obs - out["obs"]).max() <= G.OBS_TOL
+        assert np.abs(rewards - out["reward"].astype(np.float32)).max() <= 1e-5
+        for i in np.nonzero(dones)[0]:
+            ep_info.append(infos[i]["episode"])
+            if infos[i].get("TimeLimit.truncated", False):
+                with torch.no_grad():
+                    rewards[i] += 0.99 * value(torch.as_tensor(infos[i]["terminal_observation"]).cuda()).item()
+                n_boot += 1
+            assert infos[i]["episode"]["l"] == int(out["fin_len"][i]) and abs(infos[i]["episode"]["r"] - out["fin_ret"][i]) < 1e-5
+        buf_obs[t], buf_rew[t] = obs, rewards
+        obs = new_obs
+    assert len(ep_info) >= N * (n_steps // tl) - N and n_boot > 0
+    assert np.isfinite(buf_obs).all() and np.isfinite(buf_rew).all()
