@@ -453,11 +453,13 @@ RLR_DEV void rhs6r(const Sys6::Ctx& c, const double (&q)[4], const double (&wv)[
 #if RLR_EXACT
     const double nq = sqrt(n2);
     const double x = q1 / nq, yy = q2 / nq, z = q3 / nq, w = q0 / nq;
-#else
-    const double rn = rsqrt_(n2);
-    const double x = q1 * rn, yy = q2 * rn, z = q3 * rn, w = q0 * rn;
-#endif
     const double inv_m = rcp_(m);
+#else
+    // R(q/|q|) = R(q) / |q|^2 (every entry is quadratic in q): build R from the raw quaternion and fold 1/|q|^2 into the
+    // 1/m factor -- one reciprocal, no rsqrt, and the products do not wait for it.
+    const double x = q1, yy = q2, z = q3, w = q0;
+    const double inv_m = rcp_(m * n2);
+#endif
     const double x2 = x * x, y2 = yy * yy, z2 = z * z, w2 = w * w;
     const double xy = x * yy, zw = z * w, xz = x * z, yw = yy * w, yz = yy * z, xw = x * w;
     const double R00 = x2 - y2 - z2 + w2, R01 = 2 * (xy - zw), R02 = 2 * (xz + yw);
@@ -474,23 +476,30 @@ RLR_DEV void rhs6r(const Sys6::Ctx& c, const double (&q)[4], const double (&wv)[
     d[5] = 0.5 * ((wy * q0 + (-wz) * q1) + wx * q3);
     d[6] = 0.5 * ((wz * q0 + wy * q1) + (-wx) * q2);
     const double J0 = 75350.25, J1 = 6037675.13, J2 = 6037675.13;
+#if RLR_EXACT
     const double Jw0 = J0 * wx, Jw1 = J1 * wy, Jw2 = J2 * wz;
     const double c0 = wy * Jw2 - wz * Jw1, c1 = wz * Jw0 - wx * Jw2, c2 = wx * Jw1 - wy * Jw0;
     d[7] = (1.0 / J0) * (0.0 - c0);
     d[8] = (1.0 / J1) * (c.tau1 - c1);
     d[9] = (1.0 / J2) * (c.tau2 - c2);
+#else
+    // w x (J w) with J = diag(J0, J1, J1): component 0 vanishes, the others are (J0 - J1) wx wz and (J1 - J0) wx wy
+    d[7] = 0.0;
+    d[8] = (1.0 / J1) * c.tau1 - (((J0 - J2) / J1) * wx) * wz;
+    d[9] = (1.0 / J2) * c.tau2 - (((J1 - J0) / J2) * wx) * wy;
+#endif
 }
 
 constexpr int BS6 = 64;                                   // threads per block of the 6DOF kernels (compile time: LDS offsets are immediates)
-constexpr int KROW = 10 * BS6;                            // doubles between consecutive stages
-constexpr size_t SMEM6_BYTES = 6 * KROW * sizeof(double); // 30 KB per block
+constexpr int KROW = 5 * BS6;                             // double2 slots between consecutive stages (10 doubles per thread and stage)
+constexpr size_t SMEM6_BYTES = 6 * KROW * sizeof(double2); // 30 KB per block
 
 // Terminal ground event of the 6DOF solve (ivp.py:678-699): dense output Q = K^T P (rk.py:554-565, :715-737), Brent root on the
 // height polynomial, final state y(t_e).  buf = [y(14) | K6(10) | v_new(3) | dm, t_old, h, t_new]; y(t_e) is written to buf[0..13].
 // K0..K5 come from shared memory.  P[.][0] = (1,0,..,0) and P[1][.] = 0 make those terms exact no-ops, so every component needs
 // three independent 6-term FMA chains; the position rows of K are the stage velocities, recomputed from the dv rows.
-__device__ __noinline__ void event_path6(const double* __restrict__ sKt, double* __restrict__ buf) {
-#define KS(j, cc) sKt[(j) * KROW + (cc) * BS6]
+__device__ __noinline__ void event_path6(const double2* __restrict__ sKt, double* __restrict__ buf) {
+#define KS(j, cc) (((cc) & 1) ? sKt[(j) * KROW + ((cc) >> 1) * BS6].y : sKt[(j) * KROW + ((cc) >> 1) * BS6].x)
     const double dm = buf[27], t = buf[28], h = buf[29], t_new = buf[30];
     double vs[5][3];                       // stage velocities 2..5 (K_1 has zero weight in P)
 #pragma unroll
@@ -528,17 +537,18 @@ __device__ __noinline__ void event_path6(const double* __restrict__ sKt, double*
 // each: dv, dq, dw -- dr is the stage velocity, dm a per-step constant) live in shared memory at
 // sK[(stage*10 + c) * BS6 + tid]: consecutive threads -> consecutive 8-byte words (conflict-free), a fixed stride between
 // stages so that the stage loop walks one pointer.  K0 is f(y) (FSAL), K6 = f(y_new) stays in registers until accepted.
-RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&y)[14], int& natt, double* __restrict__ sKt) {
-    // sKt = sK + tid
+RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&y)[14], int& natt, double2* __restrict__ sKt) {
+    // sKt = (double2*)sK + tid; slot (stage, pair p) holds components 2p, 2p+1 -> 128-bit shared-memory accesses
     constexpr double rtol = 1e-3, atol = 1e-6;
-#define KS(j, cc) sKt[(j) * KROW + (cc) * BS6]
+#define KS2(j, p) sKt[(j) * KROW + (p) * BS6]
+#define KS(j, cc) (((cc) & 1) ? KS2(j, (cc) >> 1).y : KS2(j, (cc) >> 1).x)
     double kk[10];
     {
         const double q[4] = {y[6], y[7], y[8], y[9]};
         const double wv[3] = {y[10], y[11], y[12]};
         rhs6r(c, q, wv, y[13], kk);
 #pragma unroll
-        for (int cc = 0; cc < 10; ++cc) KS(0, cc) = kk[cc];
+        for (int p = 0; p < 5; ++p) KS2(0, p) = make_double2(kk[2 * p], kk[2 * p + 1]);
     }
     natt = 0;
     // ---- select_initial_step (common.py:68-134) on the full 14-vector f0 = [v, dv, dq, dw, dm]
@@ -616,14 +626,14 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
             double acc[10];
             double a = c_RKA[s][0];
 #pragma unroll
-            for (int cc = 0; cc < 10; ++cc) acc[cc] = KS(0, cc) * a;
+            for (int p = 0; p < 5; ++p) { const double2 k2 = KS2(0, p); acc[2 * p] = k2.x * a; acc[2 * p + 1] = k2.y * a; }
             double accm = c.dm * a;
-            const double* kp = sKt + KROW;
+            const double2* kp = sKt + KROW;
 #pragma unroll 1
             for (int j = 1; j < s; ++j, kp += KROW) {
                 a = c_RKA[s][j];
 #pragma unroll
-                for (int cc = 0; cc < 10; ++cc) acc[cc] += kp[cc * BS6] * a;
+                for (int p = 0; p < 5; ++p) { const double2 k2 = kp[p * BS6]; acc[2 * p] += k2.x * a; acc[2 * p + 1] += k2.y * a; }
                 accm += c.dm * a;
             }
 #pragma unroll
@@ -640,9 +650,9 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
             }
             rhs6r(c, sq, sw, sm, kk);
             if (s <= 5) {
-                double* ko = sKt + s * KROW;
+                double2* ko = sKt + s * KROW;
 #pragma unroll
-                for (int cc = 0; cc < 10; ++cc) ko[cc * BS6] = kk[cc];
+                for (int p = 0; p < 5; ++p) ko[p * BS6] = make_double2(kk[2 * p], kk[2 * p + 1]);
             }
         }
         // ---- error norm (rk.py:101-107): components in index order r, v, q, w, m
@@ -656,13 +666,19 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
             ssum += e * e;
         }
 #pragma unroll
-        for (int cc = 0; cc < 10; ++cc) {
-            const double yo = y[3 + cc];
-            const double yn = (cc < 3) ? sv[cc] : ((cc < 7) ? sq[cc - 3] : sw[cc - 7]);
-            const double sc = atol + fmax(fabs(yo), fabs(yn)) * rtol;
-            const double es = ((((KS(0, cc) * E0 + KS(2, cc) * E2) + KS(3, cc) * E3) + KS(4, cc) * E4) + KS(5, cc) * E5) + kk[cc] * E6;
-            const double e = RLR_DIV(es * h, sc);
-            ssum += e * e;
+        for (int p = 0; p < 5; ++p) {
+            const double2 k0 = KS2(0, p), k2 = KS2(2, p), k3 = KS2(3, p), k4 = KS2(4, p), k5 = KS2(5, p);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int cc = 2 * p + hh;
+                const double yo = y[3 + cc];
+                const double yn = (cc < 3) ? sv[cc] : ((cc < 7) ? sq[cc - 3] : sw[cc - 7]);
+                const double sc = atol + fmax(fabs(yo), fabs(yn)) * rtol;
+                const double es = hh ? (((((k0.y * E0 + k2.y * E2) + k3.y * E3) + k4.y * E4) + k5.y * E5) + kk[cc] * E6)
+                                     : (((((k0.x * E0 + k2.x * E2) + k3.x * E3) + k4.x * E4) + k5.x * E5) + kk[cc] * E6);
+                const double e = RLR_DIV(es * h, sc);
+                ssum += e * e;
+            }
         }
         {
             const double dm = c.dm;
@@ -699,7 +715,7 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
             for (int i = 0; i < 4; ++i) y[6 + i] = sq[i];
             y[13] = sm;
 #pragma unroll
-            for (int cc = 0; cc < 10; ++cc) KS(0, cc) = kk[cc];     // FSAL: f(y_new) becomes K0
+            for (int p = 0; p < 5; ++p) KS2(0, p) = make_double2(kk[2 * p], kk[2 * p + 1]);     // FSAL: f(y_new) becomes K0
             t = t_new;
             if (t - t_bound >= 0) { status = 0; break; }
             rejected = false;
@@ -711,6 +727,7 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
         }
     }
 #undef KS
+#undef KS2
     return status;
 }
 
@@ -947,7 +964,7 @@ RLR_DEV void env_step(const RlrParams& p, EnvState<S>& st, const float (&u)[3], 
     const double t = (double)((long long)st.k * (long long)p.dt_ms) / 1000.0;   // round(t + dt, 3)  (simulator.py:245)
     int natt;
     int status;
-    if constexpr (S::N == 14) status = rk45_solve6(c, t, t + p.dt, st.y, natt, sK + threadIdx.x);
+    if constexpr (S::N == 14) status = rk45_solve6(c, t, t + p.dt, st.y, natt, reinterpret_cast<double2*>(sK) + threadIdx.x);
     else status = rk45_solve<S>(c, t, t + p.dt, st.y, natt);
     float s[S::N];
     if constexpr (S::N == 14) {
