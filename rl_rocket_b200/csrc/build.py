@@ -16,7 +16,7 @@ _V = os.environ.get("RLR_VARIANT", "A")
 OUT = os.path.join(OUT_DIR, "librlrocket.so" if _V == "A" else f"librlrocket_{_V}.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-VARIANT = {"A": [], "B": ["-DRLR_REGS6=96"], "C": ["-DRLR_REGS6=160"]}[os.environ.get("RLR_VARIANT", "A")]     # tuning builds
+VARIANT = os.environ.get("RLR_DEFS", "").split()     # tuning builds: RLR_VARIANT=<tag> RLR_DEFS="-DRLR_REGS6=144 ..." -> librlrocket_<tag>.so
 COMMON = VARIANT + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", HERE]
 UNITS = [("kernels_exact.cu", ["-fmad=false"]), ("kernels_fast.cu", ["-fmad=true"]), ("fma_peak.cu", []), ("abi.cu", [])]
 

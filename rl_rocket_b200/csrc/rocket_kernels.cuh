@@ -30,10 +30,41 @@
 #ifndef RLR_NS
 #error "define RLR_NS before including rocket_kernels.cuh"
 #endif
+#ifndef RLR_EVENT_NEWTON
+#define RLR_EVENT_NEWTON (!RLR_EXACT)   // fast build: Newton root of the height quartic, Brent as the fallback (see event_path6)
+#endif
+#ifndef RLR_PHILOX_UNROLL
+#define RLR_PHILOX_UNROLL 0
+#endif
+#ifndef RLR_STAGE_UNROLL
+#define RLR_STAGE_UNROLL 0           // 1: the six RK stages as one basic block -- measured slower (spills at 128 registers)
+#endif
 
 namespace RLR_NS {
 
 #define RLR_DEV __device__ __forceinline__
+
+// Development aid (tuning builds only, -DRLR_PHASE_TIMING=1): per-warp clock64() deltas between phase marks, summed / maxed per phase.
+#ifndef RLR_PHASE_TIMING
+#define RLR_PHASE_TIMING 0
+#endif
+#if RLR_PHASE_TIMING
+__device__ unsigned long long g_phase_sum[16], g_phase_max[16], g_phase_cnt[16];
+RLR_DEV void phase_mark(int k) {
+    __shared__ long long tp[8];
+    if ((threadIdx.x & 31) == 0) {
+        const long long now = clock64();
+        if (k >= 0) {
+            const unsigned long long d = (unsigned long long)(now - tp[threadIdx.x >> 5]);
+            atomicAdd(&g_phase_sum[k], d); atomicMax(&g_phase_max[k], d); atomicAdd(&g_phase_cnt[k], 1ull);
+        }
+        tp[threadIdx.x >> 5] = now;
+    }
+}
+#define RLR_PHASE(k) phase_mark(k)
+#else
+#define RLR_PHASE(k)
+#endif
 
 // ------------------------------------------------------------------ numpy float32 helpers
 // numpy's SIMD float32 sin/cos for |x| < pi/4 (5-FMA Horner). Explicit fmaf:
@@ -98,6 +129,20 @@ RLR_DEV double rcp_(double x) {
     r = fma(r, e, r);
     return r;
 }
+// reciprocal of an error-control scale (atol + rtol |y|): hardware seed + RLR_RCP1_NEWTON Newton steps.  These factors only
+// weight the RMS norms that choose the step size, where a relative error of 1e-12 moves h by 1e-13 and the state by < 1e-15.
+#ifndef RLR_RCP1_NEWTON
+#define RLR_RCP1_NEWTON 1
+#endif
+RLR_DEV double rcp1_(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#pragma unroll
+    for (int it = 0; it < RLR_RCP1_NEWTON; ++it) { const double e = fma(-x, r, 1.0); r = fma(r, e, r); }
+    return r;
+}
+// max(|a|, |b|) with one compare and two selects (fmax() expands to a NaN-aware six-instruction sequence)
+RLR_DEV double absmax_(double a, double b) { const double fa = fabs(a), fb = fabs(b); return (fa > fb) ? fa : fb; }
 RLR_DEV double rsqrt_(double x) {
     double r;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
@@ -443,23 +488,20 @@ __constant__ double c_RKA[7][6] = {
     {B0, 0, B2, B3, B4, B5}};
 __constant__ double c_RKB[6] = {B0, 0, B2, B3, B4, B5};
 __constant__ double c_RKE[7] = {E0, 0, E2, E3, E4, E5, E6};
+__constant__ double c_RKC[7] = {0, 1.0 / 5, 3.0 / 10, 4.0 / 5, 8.0 / 9, 1, 1};      // nodes c_s = sum_j a_sj (rk.py:282)
+#define RLR_INV_RS14 0.2672612419124243846      // 1 / sqrt(14)
 
 // Right-hand side restricted to the components that need arithmetic: d = [dv(3), dq(4), dw(3)].
 // dr is the stage velocity itself and dm is constant over the env step (simulator.py:280, :291-292).
 RLR_DEV void rhs6r(const Sys6::Ctx& c, const double (&q)[4], const double (&wv)[3], double m, double (&d)[10]) {
     const double q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3];
     const double wx = wv[0], wy = wv[1], wz = wv[2];
-    const double n2 = q1 * q1 + q2 * q2 + q3 * q3 + q0 * q0;
+    const double J0 = 75350.25, J1 = 6037675.13, J2 = 6037675.13;
 #if RLR_EXACT
+    const double n2 = q1 * q1 + q2 * q2 + q3 * q3 + q0 * q0;
     const double nq = sqrt(n2);
     const double x = q1 / nq, yy = q2 / nq, z = q3 / nq, w = q0 / nq;
     const double inv_m = rcp_(m);
-#else
-    // R(q/|q|) = R(q) / |q|^2 (every entry is quadratic in q): build R from the raw quaternion and fold 1/|q|^2 into the
-    // 1/m factor -- one reciprocal, no rsqrt, and the products do not wait for it.
-    const double x = q1, yy = q2, z = q3, w = q0;
-    const double inv_m = rcp_(m * n2);
-#endif
     const double x2 = x * x, y2 = yy * yy, z2 = z * z, w2 = w * w;
     const double xy = x * yy, zw = z * w, xz = x * z, yw = yy * w, yz = yy * z, xw = x * w;
     const double R00 = x2 - y2 - z2 + w2, R01 = 2 * (xy - zw), R02 = 2 * (xz + yw);
@@ -475,14 +517,32 @@ RLR_DEV void rhs6r(const Sys6::Ctx& c, const double (&q)[4], const double (&wv)[
     d[4] = 0.5 * ((wx * q0 + wz * q2) + (-wy) * q3);
     d[5] = 0.5 * ((wy * q0 + (-wz) * q1) + wx * q3);
     d[6] = 0.5 * ((wz * q0 + wy * q1) + (-wx) * q2);
-    const double J0 = 75350.25, J1 = 6037675.13, J2 = 6037675.13;
-#if RLR_EXACT
     const double Jw0 = J0 * wx, Jw1 = J1 * wy, Jw2 = J2 * wz;
     const double c0 = wy * Jw2 - wz * Jw1, c1 = wz * Jw0 - wx * Jw2, c2 = wx * Jw1 - wy * Jw0;
     d[7] = (1.0 / J0) * (0.0 - c0);
     d[8] = (1.0 / J1) * (c.tau1 - c1);
     d[9] = (1.0 / J2) * (c.tau2 - c2);
 #else
+    // R(q/|q|) Tb = [(w^2 - u.u) Tb + 2 (u.Tb) u + 2 w (u x Tb)] / |q|^2  with q = (w, u): 23 operations instead of the 37 of the
+    // explicit rotation matrix, one reciprocal (1 / (m |q|^2)), no rsqrt, and the products do not wait for it.
+    const double w = q0, x = q1, yy = q2, z = q3;
+    const double uu = (x * x + yy * yy) + z * z;
+    const double inv_m = rcp_(m * (uu + w * w));
+    const double a = w * w - uu;
+    const double b = 2.0 * ((x * c.Tb0 + yy * c.Tb1) + z * c.Tb2);
+    const double w2 = w + w;
+    const double cx = yy * c.Tb2 - z * c.Tb1, cy = z * c.Tb0 - x * c.Tb2, cz = x * c.Tb1 - yy * c.Tb0;
+    const double F0 = (a * c.Tb0 + b * x) + w2 * cx;
+    const double F1 = (a * c.Tb1 + b * yy) + w2 * cy;
+    const double F2 = (a * c.Tb2 + b * z) + w2 * cz;
+    d[0] = inv_m * F0 + (-9.81);
+    d[1] = inv_m * F1;
+    d[2] = inv_m * F2;
+    const double hx = 0.5 * wx, hy = 0.5 * wy, hz = 0.5 * wz;
+    d[3] = ((-hx) * q1 + (-hy) * q2) + (-hz) * q3;
+    d[4] = (hx * q0 + hz * q2) + (-hy) * q3;
+    d[5] = (hy * q0 + (-hz) * q1) + hx * q3;
+    d[6] = (hz * q0 + hy * q1) + (-hx) * q2;
     // w x (J w) with J = diag(J0, J1, J1): component 0 vanishes, the others are (J0 - J1) wx wz and (J1 - J0) wx wy
     d[7] = 0.0;
     d[8] = (1.0 / J1) * c.tau1 - (((J0 - J2) / J1) * wx) * wz;
@@ -515,10 +575,38 @@ __device__ __noinline__ void event_path6(const double2* __restrict__ sKt, double
 #define DENSE_Q(k0, k2, k3, k4, k5, k6, cc) \
     ((((((k0) * c_P[0][cc] + (k2) * c_P[2][cc]) + (k3) * c_P[3][cc]) + (k4) * c_P[4][cc]) + (k5) * c_P[5][cc]) + (k6) * c_P[6][cc])
     const double vx0 = buf[3], vx6 = buf[24];
-    const double root = brentq_event(vx0, DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 1),
-                                     DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 2),
-                                     DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 3), buf[0], t, h, t, t_new);
+    const double hq0 = vx0, hq1 = DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 1),
+                 hq2 = DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 2),
+                 hq3 = DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 3);
+#if RLR_EVENT_NEWTON
+    // Fast build: the root of the height quartic  g(x) = r0 + h x (q0 + x (q1 + x (q2 + x q3))),  x = (t_e - t) / h in [0, 1],  by
+    // Newton's method from the secant point (quadratic convergence: 5 steps reach the rounding floor; Brent's bisection /
+    // inverse-quadratic steps with their IEEE divisions were the longest serial chain of the launch).  Anything unexpected
+    // (non-finite, left the bracket, residual not at rounding level) falls back to brentq_event, so the result is always a
+    // root to ~4 ulp -- the same tolerance scipy's brentq (xtol = rtol = 4 eps) guarantees.
+    double xx;
+    {
+        const double g0 = buf[0];
+        const double g1 = h * (((hq0 + hq1) + hq2) + hq3) + g0;
+        double x = RLR_DIV(g0, g0 - g1);
+        double gx = 0.0;
+#pragma unroll 1
+        for (int it = 0; it < 5; ++it) {
+            const double s = fma(fma(fma(hq3, x, hq2), x, hq1), x, hq0);
+            const double ds = fma(fma(fma(4.0 * hq3, x, 3.0 * hq2), x, 2.0 * hq1), x, hq0);
+            gx = fma(h * x, s, g0);
+            x = x - RLR_DIV(gx, h * ds);
+        }
+        const double s = fma(fma(fma(hq3, x, hq2), x, hq1), x, hq0);
+        gx = fma(h * x, s, g0);
+        const double tol = 64 * 2.220446049250313e-16 * (fabs(g0) + fabs(g1));
+        if (x >= 0.0 && x <= 1.0 && fabs(gx) <= tol) xx = x;
+        else xx = RLR_DIV(brentq_event(hq0, hq1, hq2, hq3, g0, t, h, t, t_new) - t, h);
+    }
+#else
+    const double root = brentq_event(hq0, hq1, hq2, hq3, buf[0], t, h, t, t_new);
     const double xx = RLR_DIV(root - t, h);
+#endif
     const double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
 #define DENSE_Y(yold, k0, k2, k3, k4, k5, k6)                                                                \
     (h * ((((k0) * p1 + DENSE_Q(k0, k2, k3, k4, k5, k6, 1) * p2) + DENSE_Q(k0, k2, k3, k4, k5, k6, 2) * p3) + \
@@ -562,7 +650,7 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
 #if RLR_EXACT
             isc[i] = sc;
 #else
-            isc[i] = rcp_(sc);
+            isc[i] = rcp1_(sc);
 #endif
         }
 #if RLR_EXACT
@@ -575,11 +663,20 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
         for (int i = 0; i < 14; ++i) { const double u_ = SCALED(y[i], i); a0 += u_ * u_; }
 #pragma unroll
         for (int i = 0; i < 3; ++i) { const double u_ = SCALED(y[3 + i], i); a1 += u_ * u_; }
+#if RLR_EXACT
+#define RLR_LIVE(cc) true
+#else
+#define RLR_LIVE(cc) ((cc) != 7)            // d(omega_x)/dt == 0 exactly in the fast build (rhs6r)
+#endif
 #pragma unroll
-        for (int i = 0; i < 10; ++i) { const double u_ = SCALED(kk[i], 3 + i); a1 += u_ * u_; }
+        for (int i = 0; i < 10; ++i) { if (RLR_LIVE(i)) { const double u_ = SCALED(kk[i], 3 + i); a1 += u_ * u_; } }
         { const double u_ = SCALED(c.dm, 13); a1 += u_ * u_; }
+#if RLR_EXACT
         const double rs14 = sqrt(14.0);
         const double d0 = RLR_DIV(sqrt_(a0), rs14), d1 = RLR_DIV(sqrt_(a1), rs14);
+#else
+        const double d0 = sqrt_(a0) * RLR_INV_RS14, d1 = sqrt_(a1) * RLR_INV_RS14;
+#endif
         double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : RLR_DIV(0.01 * d0, d1);
         h0 = py_min(h0, interval);
         double v1[3], q1[4], w1[3], f1[10];
@@ -588,16 +685,21 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
 #pragma unroll
         for (int i = 0; i < 4; ++i) q1[i] = y[6 + i] + h0 * kk[3 + i];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) w1[i] = y[10 + i] + h0 * kk[7 + i];
+        for (int i = 0; i < 3; ++i) w1[i] = RLR_LIVE(7 + i) ? y[10 + i] + h0 * kk[7 + i] : y[10 + i];
         const double m1 = y[13] + h0 * c.dm;
         rhs6r(c, q1, w1, m1, f1);
         double a2 = 0.0;
 #pragma unroll
         for (int i = 0; i < 3; ++i) { const double u_ = SCALED(v1[i] - y[3 + i], i); a2 += u_ * u_; }
 #pragma unroll
-        for (int i = 0; i < 10; ++i) { const double u_ = SCALED(f1[i] - kk[i], 3 + i); a2 += u_ * u_; }
+        for (int i = 0; i < 10; ++i) { if (RLR_LIVE(i)) { const double u_ = SCALED(f1[i] - kk[i], 3 + i); a2 += u_ * u_; } }
+#if RLR_EXACT
         { const double u_ = SCALED(c.dm - c.dm, 13); a2 += u_ * u_; }
         const double d2 = RLR_DIV(RLR_DIV(sqrt_(a2), rs14), h0);
+#else
+        const double d2 = RLR_DIV(sqrt_(a2) * RLR_INV_RS14, h0);
+#endif
+#undef RLR_LIVE
         double h1;
         if (d1 <= 1e-15 && d2 <= 1e-15) h1 = py_max(1e-6, h0 * 1e-3);
         else h1 = pow_p02(RLR_DIV(0.01, py_max(d1, d2)));
@@ -609,6 +711,7 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
     if (h_abs < min_step) h_abs = min_step;
     bool rejected = false;
     int status;
+    RLR_PHASE(1);                       // 1: make_ctx, K0, select_initial_step
 #pragma unroll 1
     for (;;) {
         if (h_abs < min_step) { status = -1; break; }
@@ -620,22 +723,19 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
         double sv[3], sq[4], sw[3], sm = y[13], aB[3], aE[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) { aB[i] = y[3 + i] * B0; aE[i] = y[3 + i] * E0; }
-        // ---- rk_step (rk.py:14-71); stage 6 is y_new (row 6 of c_RKA = B)
-#pragma unroll 1
-        for (int s = 1; s <= 6; ++s) {
-            double acc[10];
-            double a = c_RKA[s][0];
+#if RLR_STAGE_UNROLL
+        // ---- rk_step (rk.py:14-71), stages unrolled.  The sums of stage s+1 over the rows already in shared memory are issued
+        // BEFORE the right-hand side of stage s (independent work for its reciprocal chain); the row just computed (K_s) is
+        // added from registers.  Same summation order as the rolled loop: j = 0 .. s.
+        double acc[10], accm;
+        {
+            const double a = c_RKA[1][0];
 #pragma unroll
             for (int p = 0; p < 5; ++p) { const double2 k2 = KS2(0, p); acc[2 * p] = k2.x * a; acc[2 * p + 1] = k2.y * a; }
-            double accm = c.dm * a;
-            const double2* kp = sKt + KROW;
-#pragma unroll 1
-            for (int j = 1; j < s; ++j, kp += KROW) {
-                a = c_RKA[s][j];
+            accm = c.dm * a;
+        }
 #pragma unroll
-                for (int p = 0; p < 5; ++p) { const double2 k2 = kp[p * BS6]; acc[2 * p] += k2.x * a; acc[2 * p + 1] += k2.y * a; }
-                accm += c.dm * a;
-            }
+        for (int s = 1; s <= 6; ++s) {
 #pragma unroll
             for (int i = 0; i < 3; ++i) sv[i] = y[3 + i] + acc[i] * h;
 #pragma unroll
@@ -643,6 +743,81 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
 #pragma unroll
             for (int i = 0; i < 3; ++i) sw[i] = y[10 + i] + acc[7 + i] * h;
             sm = y[13] + accm * h;
+            if (s <= 5) {
+                const double bs = c_RKB[s], es = c_RKE[s];
+#pragma unroll
+                for (int i = 0; i < 3; ++i) { aB[i] += sv[i] * bs; aE[i] += sv[i] * es; }
+                const int sn = s + 1;
+                double a = c_RKA[sn][0];
+#pragma unroll
+                for (int p = 0; p < 5; ++p) { const double2 k2 = KS2(0, p); acc[2 * p] = k2.x * a; acc[2 * p + 1] = k2.y * a; }
+                accm = c.dm * a;
+#pragma unroll
+                for (int j = 1; j < s; ++j) {
+                    a = c_RKA[sn][j];
+#pragma unroll
+                    for (int p = 0; p < 5; ++p) { const double2 k2 = KS2(j, p); acc[2 * p] += k2.x * a; acc[2 * p + 1] += k2.y * a; }
+                    accm += c.dm * a;
+                }
+            }
+            rhs6r(c, sq, sw, sm, kk);
+            if (s <= 5) {
+                const double a = c_RKA[s + 1][s];
+#pragma unroll
+                for (int p = 0; p < 5; ++p) {
+                    KS2(s, p) = make_double2(kk[2 * p], kk[2 * p + 1]);
+                    acc[2 * p] += kk[2 * p] * a; acc[2 * p + 1] += kk[2 * p + 1] * a;
+                }
+                accm += c.dm * a;
+            }
+        }
+#else
+        // ---- rk_step (rk.py:14-71); stage 6 is y_new (row 6 of c_RKA = B).
+        // Fast build: d(omega_x)/dt is identically zero (J_y == J_z, see rhs6r), so component 7 of the stage matrix is skipped and
+        // omega_x keeps its value; dm is constant, so the mass stage value is m + (c_s h) dm.
+#if RLR_EXACT
+#define RLR_LIVE(cc) true
+#else
+#define RLR_LIVE(cc) ((cc) != 7)
+#endif
+#pragma unroll 1
+        for (int s = 1; s <= 6; ++s) {
+            double acc[10];
+            double a = c_RKA[s][0];
+#pragma unroll
+            for (int p = 0; p < 5; ++p) {
+                const double2 k2 = KS2(0, p);
+                acc[2 * p] = k2.x * a;
+                if (RLR_LIVE(2 * p + 1)) acc[2 * p + 1] = k2.y * a;
+            }
+#if RLR_EXACT
+            double accm = c.dm * a;
+#endif
+            const double2* kp = sKt + KROW;
+#pragma unroll 1
+            for (int j = 1; j < s; ++j, kp += KROW) {
+                a = c_RKA[s][j];
+#pragma unroll
+                for (int p = 0; p < 5; ++p) {
+                    const double2 k2 = kp[p * BS6];
+                    acc[2 * p] += k2.x * a;
+                    if (RLR_LIVE(2 * p + 1)) acc[2 * p + 1] += k2.y * a;
+                }
+#if RLR_EXACT
+                accm += c.dm * a;
+#endif
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sv[i] = y[3 + i] + acc[i] * h;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sq[i] = y[6 + i] + acc[3 + i] * h;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sw[i] = RLR_LIVE(7 + i) ? y[10 + i] + acc[7 + i] * h : y[10 + i];
+#if RLR_EXACT
+            sm = y[13] + accm * h;
+#else
+            sm = y[13] + (c_RKC[s] * h) * c.dm;
+#endif
             if (s <= 5) {
                 const double bs = c_RKB[s], es = c_RKE[s];
 #pragma unroll
@@ -655,14 +830,19 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
                 for (int p = 0; p < 5; ++p) ko[p * BS6] = make_double2(kk[2 * p], kk[2 * p + 1]);
             }
         }
+#endif
         // ---- error norm (rk.py:101-107): components in index order r, v, q, w, m
         double rn[3];
         double ssum = 0.0;
+#if RLR_EXACT
+#define RLR_ERR_TERM(num, yo, yn) ((num) / (atol + fmax(fabs(yo), fabs(yn)) * rtol))
+#else
+#define RLR_ERR_TERM(num, yo, yn) ((num) * rcp1_(fma(absmax_(yo, yn), rtol, atol)))
+#endif
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             rn[i] = y[i] + h * aB[i];
-            const double sc = atol + fmax(fabs(y[i]), fabs(rn[i])) * rtol;
-            const double e = RLR_DIV((aE[i] + sv[i] * E6) * h, sc);
+            const double e = RLR_ERR_TERM((aE[i] + sv[i] * E6) * h, y[i], rn[i]);
             ssum += e * e;
         }
 #pragma unroll
@@ -671,23 +851,28 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
 #pragma unroll
             for (int hh = 0; hh < 2; ++hh) {
                 const int cc = 2 * p + hh;
+                if (!RLR_LIVE(cc)) continue;          // K rows of omega_x are exactly zero in the fast build
                 const double yo = y[3 + cc];
                 const double yn = (cc < 3) ? sv[cc] : ((cc < 7) ? sq[cc - 3] : sw[cc - 7]);
-                const double sc = atol + fmax(fabs(yo), fabs(yn)) * rtol;
                 const double es = hh ? (((((k0.y * E0 + k2.y * E2) + k3.y * E3) + k4.y * E4) + k5.y * E5) + kk[cc] * E6)
                                      : (((((k0.x * E0 + k2.x * E2) + k3.x * E3) + k4.x * E4) + k5.x * E5) + kk[cc] * E6);
-                const double e = RLR_DIV(es * h, sc);
+                const double e = RLR_ERR_TERM(es * h, yo, yn);
                 ssum += e * e;
             }
         }
+#if RLR_EXACT
         {
             const double dm = c.dm;
             const double es = (((((dm * E0 + dm * 0.0) + dm * E2) + dm * E3) + dm * E4) + dm * E5) + dm * E6;
-            const double sc = atol + fmax(fabs(y[13]), fabs(sm)) * rtol;
-            const double e = RLR_DIV(es * h, sc);
+            const double e = RLR_ERR_TERM(es * h, y[13], sm);
             ssum += e * e;
         }
         const double err = RLR_DIV(sqrt_(ssum), sqrt(14.0));
+#else
+        // the error weights sum to zero: a constant derivative (the mass) contributes |dm| * O(1e-17) -- dropped
+        const double err = sqrt_(ssum) * RLR_INV_RS14;
+#endif
+#undef RLR_ERR_TERM
         if (err < 1) {
             double factor = (err == 0) ? 10.0 : py_min(10.0, 0.9 * pow_m02(err));
             if (rejected) factor = py_min(1.0, factor);
@@ -703,6 +888,7 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
 #pragma unroll
                 for (int i = 0; i < 3; ++i) ebuf[24 + i] = sv[i];
                 ebuf[27] = c.dm; ebuf[28] = t; ebuf[29] = h; ebuf[30] = t_new;
+                RLR_PHASE(2);           // 2: RK attempts (all of them when the step ends in an event)
                 event_path6(sKt, ebuf);
 #pragma unroll
                 for (int i = 0; i < 14; ++i) y[i] = ebuf[i];
@@ -726,8 +912,11 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
             rejected = true;
         }
     }
+#undef RLR_LIVE
 #undef KS
 #undef KS2
+    if (status != 1) { RLR_PHASE(2); }
+    RLR_PHASE(3);                       // 3: event path (dense output + root) -- ~0 for warps without an event
     return status;
 }
 
@@ -745,7 +934,11 @@ RLR_DEV void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
 
 template <int N>
 RLR_DEV void sample_ic(const RlrParams& p, uint64_t seed, int64_t env, int32_t episode, float (&ic)[N]) {
+#if RLR_PHILOX_UNROLL
+#pragma unroll
+#else
 #pragma unroll 1
+#endif
     for (int b = 0; b * 2 < N; ++b) {      // rolled: the reset path is rare per thread, keep its code small
         uint32_t c[4] = {(uint32_t)b, (uint32_t)episode, (uint32_t)((uint64_t)env & 0xffffffffu), (uint32_t)((uint64_t)env >> 32)};
         philox4x32_10(c, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
@@ -1085,6 +1278,7 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
     StepFlags fl = {0, 0, 0, 0, 0, 0};
     int ep_len = 0;
     double ep_ret = 0.0;
+    RLR_PHASE(-1);
     if (active) {
         EnvState<S> st;
         load_state<S>(gs, n, i, st);
@@ -1092,7 +1286,9 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
         map_action<S>(p, actions, action_kind, i, u, a_thr);
         float obs[S::N];
         StepRes res;
+        RLR_PHASE(0);                   // 0: state / action loads
         env_step<S>(p, st, u, a_thr, obs, res, fl, sK);
+        RLR_PHASE(4);                   // 4: normalise, obs, reward
         ep_len = st.k; ep_ret = st.ep_ret;
         if (out.reward) out.reward[i] = (float)res.reward;
         if (out.reward64) out.reward64[i] = res.reward;
@@ -1109,16 +1305,19 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
 #pragma unroll
             for (int c = 0; c < S::N; ++c) yp[c * n + i] = st.y[c];
         }
+        RLR_PHASE(5);                   // 5: per-step output stores
         if (fl.done) {
             if (out.terminal_obs) write_obs<S>(p, out.terminal_obs, i, obs);
             if (out.fin_ret) out.fin_ret[i] = st.ep_ret;
             if (out.fin_len) out.fin_len[i] = st.k;
             finish_and_reset<S>(p, st, ic_inject, i, env_offset, seed, obs);
         }
+        RLR_PHASE(6);                   // 6: auto-reset
         write_obs<S>(p, out.obs, i, obs);
         store_state<S>(gs, n, i, st);
     }
     accumulate_stats(out.stats, active, fl, ep_len, ep_ret);
+    RLR_PHASE(7);                       // 7: obs / state stores, statistics
 }
 
 template <class S>
@@ -1182,6 +1381,13 @@ __global__ void RLR_KERNEL_BOUNDS(S) rollout_kernel(const __grid_constant__ RlrP
     }
 }
 
+#ifndef RLR_PAIR6
+#define RLR_PAIR6 0                 // 1: warp-specialised two-threads-per-environment 6DOF kernels (rocket_pair6.cuh) -- measured slower
+#endif
+#if RLR_PAIR6
+#include "experimental/rocket_pair6.cuh"
+#endif
+
 // ------------------------------------------------------------------ host launchers (called from abi.cu)
 // Launch geometry.  6DOF: 64-thread blocks, 30 KB of dynamic shared memory each (stage matrix).  The number of co-resident
 // blocks per SM comes from the occupancy calculator; when the grid would end in a nearly empty last wave, residency is
@@ -1237,6 +1443,16 @@ inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block
 int launch_step(const RlrParams* p, RlrState st, const void* actions, int action_kind, const float* ic_inject, RlrStepOut out, int64_t n,
                 int64_t env_offset, uint64_t seed, cudaStream_t stream) {
     if (p->dof == 6) {
+#if RLR_PAIR6
+        static bool carveout_set = false;
+        if (!carveout_set) {
+            cudaFuncSetAttribute(pair6::pair_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            carveout_set = true;
+        }
+        pair6::pair_step_kernel<<<grid_for(n, pair6::ENVS), pair6::THREADS, pair6::SMEM_BYTES, stream>>>(
+            *p, st, (const float*)actions, action_kind, ic_inject, out, n, env_offset, seed);
+        return (int)cudaGetLastError();
+#endif
         const Geometry g = pick_geometry(step_kernel<Sys6>, n, BS6, SMEM6_BYTES);
         step_kernel<Sys6><<<grid_for(n, g.block), g.block, g.smem, stream>>>(*p, st, actions, action_kind, ic_inject, out, n, env_offset, seed);
     } else {
@@ -1257,6 +1473,16 @@ int launch_rollout(const RlrParams* p, RlrState st, const void* actions, int act
                    uint8_t* done_buf, uint8_t* trunc_buf, float* last_obs, unsigned long long* stats, int64_t n, int64_t env_offset,
                    uint64_t seed, cudaStream_t stream) {
     if (p->dof == 6) {
+#if RLR_PAIR6
+        static bool carveout_set = false;
+        if (!carveout_set) {
+            cudaFuncSetAttribute(pair6::pair_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            carveout_set = true;
+        }
+        pair6::pair_rollout_kernel<<<grid_for(n, pair6::ENVS), pair6::THREADS, pair6::SMEM_BYTES, stream>>>(
+            *p, st, (const float*)actions, action_kind, T, obs_buf, reward_buf, done_buf, trunc_buf, last_obs, stats, n, env_offset, seed);
+        return (int)cudaGetLastError();
+#endif
         const Geometry g = pick_geometry(rollout_kernel<Sys6>, n, BS6, SMEM6_BYTES);
         rollout_kernel<Sys6><<<grid_for(n, g.block), g.block, g.smem, stream>>>(*p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf,
                                                                               trunc_buf, last_obs, stats, n, env_offset, seed);
