@@ -955,6 +955,40 @@ RLR_DEV void sample_ic(const RlrParams& p, uint64_t seed, int64_t env, int32_t e
     }
 }
 
+// Warp-cooperative version of sample_ic for the in-kernel auto-reset: only ~1.4 % of the lanes finish an episode in a given step,
+// but a lane that does would walk the N/2 Philox blocks one after the other while the other 31 lanes wait (7.4 k cycles per warp
+// with a reset, profiles/r01c).  Here lane b computes block b of the resetting lane's initial condition and the 2 x N/2 values
+// are handed over with shuffles: one Philox latency per resetting lane.  Same counters, same bits, same arithmetic as sample_ic.
+// Must be called by all 32 lanes (warp-uniform); fills `ic` of the lanes with need == true.
+template <int N>
+RLR_DEV void sample_ic_warp(const RlrParams& p, uint64_t seed, int64_t env, int32_t episode, bool need, float (&ic)[N]) {
+    constexpr int NB = (N + 1) / 2;
+    const int lane = threadIdx.x & 31;
+    unsigned todo = __ballot_sync(0xffffffffu, need);
+    while (todo) {                                   // warp-uniform
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const long long env_s = __shfl_sync(0xffffffffu, (long long)env, src);
+        const int ep_s = __shfl_sync(0xffffffffu, episode, src);
+        float f0 = 0.0f, f1 = 0.0f;
+        if (lane < NB) {
+            uint32_t c[4] = {(uint32_t)lane, (uint32_t)ep_s, (uint32_t)((uint64_t)env_s & 0xffffffffu), (uint32_t)((uint64_t)env_s >> 32)};
+            philox4x32_10(c, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+            const int j0 = 2 * lane, j1 = (2 * lane + 1 < N) ? 2 * lane + 1 : 2 * lane;
+            const uint64_t b0 = ((uint64_t)c[0] << 32) | (uint64_t)c[1], b1 = ((uint64_t)c[2] << 32) | (uint64_t)c[3];
+            const double u0 = (double)(b0 >> 11) * 0x1.0p-53, u1 = (double)(b1 >> 11) * 0x1.0p-53;
+            const double lo0 = (double)p.ic_low[j0], hi0 = (double)p.ic_high[j0], lo1 = (double)p.ic_low[j1], hi1 = (double)p.ic_high[j1];
+            f0 = (float)(lo0 + (hi0 - lo0) * u0);
+            f1 = (float)(lo1 + (hi1 - lo1) * u1);
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const float v = __shfl_sync(0xffffffffu, (j & 1) ? f1 : f0, j >> 1);
+            if (lane == src) ic[j] = v;
+        }
+    }
+}
+
 // reset from an f32 IC: quaternion normalised in f32 (rocket_env.py:673), v0 = f32 norm of IC velocity
 template <class S>
 RLR_DEV void reset_from_ic(const RlrParams& p, float (&ic)[S::N], double (&y)[S::N], float& v0, float (&obs)[S::N]) {
@@ -1033,9 +1067,13 @@ RLR_DEV void reward6(const RlrParams& p, const float (&s)[14], const float* u, f
     // The Euler angles are only compared with limits: |atan2(b, a)| > L  <=>  a < cos(L) * hypot(a, b)  (cos is decreasing on
     // [0, pi]) and |asin(v)| > L  <=>  |v| > sin(L); cos(L) / sin(L) come precomputed from the host (with sentinels for limits
     // outside [0, pi] resp. [0, pi/2]), so no atan2 / asin is evaluated.
-    const double hy0 = sqrt_(R00 * R00 + R01 * R01), hy2 = sqrt_(R22 * R22 + R12 * R12), av1 = fabs(R02);
-    const int att_viol = (R00 < p.att_traj_c[0] * hy0) | (av1 > p.att_traj_c[1]) | (R22 < p.att_traj_c[2] * hy2);
-    const int att_ok = (R00 > p.att_land_c[0] * hy0) | (av1 < p.att_land_c[1]) | (R22 > p.att_land_c[2] * hy2);
+    // a < c * hypot(a, b) without the square root:  sign(a) a^2 < sign(c) c^2 (a^2 + b^2)  (x -> sign(x) x^2 is increasing)
+    const double h0sq = R00 * R00 + R01 * R01, h2sq = R22 * R22 + R12 * R12, av1 = fabs(R02);
+    const double s00 = R00 * fabs(R00), s22 = R22 * fabs(R22);
+    const double t0c = p.att_traj_c[0] * fabs(p.att_traj_c[0]), t2c = p.att_traj_c[2] * fabs(p.att_traj_c[2]);
+    const double l0c = p.att_land_c[0] * fabs(p.att_land_c[0]), l2c = p.att_land_c[2] * fabs(p.att_land_c[2]);
+    const int att_viol = (s00 < t0c * h0sq) | (av1 > p.att_traj_c[1]) | (s22 < t2c * h2sq);
+    const int att_ok = (s00 > l0c * h0sq) | (av1 < p.att_land_c[1]) | (s22 > l2c * h2sq);
 #endif
     const int om_ok = ((double)fabsf(s[10]) < p.omega_lim[0]) | ((double)fabsf(s[11]) < p.omega_lim[1]) | ((double)fabsf(s[12]) < p.omega_lim[2]);
     const float rn = f32_norm3(s[0], s[1], s[2]), vn = f32_norm3(s[3], s[4], s[5]);
@@ -1194,16 +1232,16 @@ RLR_DEV void env_step(const RlrParams& p, EnvState<S>& st, const float (&u)[3], 
 // ------------------------------------------------------------------ kernels
 template <class S>
 RLR_DEV void load_state(const RlrState& gs, int64_t n, int64_t i, EnvState<S>& st) {
-    const double* y = (const double*)gs.y;
+    const double* y = (const double*)gs.y + i;
 #pragma unroll
-    for (int c = 0; c < S::N; ++c) st.y[c] = y[c * n + i];
+    for (int c = 0; c < S::N; ++c, y += n) st.y[c] = *y;
     st.k = gs.k[i]; st.episode = gs.episode[i]; st.v0 = gs.v0[i]; st.ep_ret = gs.ep_ret[i];
 }
 template <class S>
 RLR_DEV void store_state(const RlrState& gs, int64_t n, int64_t i, const EnvState<S>& st) {
-    double* y = (double*)gs.y;
+    double* y = (double*)gs.y + i;
 #pragma unroll
-    for (int c = 0; c < S::N; ++c) y[c * n + i] = st.y[c];
+    for (int c = 0; c < S::N; ++c, y += n) *y = st.y[c];
     gs.k[i] = st.k; gs.episode[i] = st.episode; gs.v0[i] = st.v0; gs.ep_ret[i] = st.ep_ret;
 }
 
@@ -1216,8 +1254,8 @@ RLR_DEV void write_obs(const RlrParams& p, float* dst, int64_t i, const float (&
     }
 }
 
-// warp-shuffle reduction of the episode statistics: counters packed into one 64-bit word (5 x 6-bit counts of <= 32 lanes
-// + attempts in the upper bits), lengths and fixed-point returns in two more; lane 0 issues one atomic per non-zero slot.
+// warp reduction of the episode statistics (REDUX for the 32-bit counters, shuffles for the 64-bit fixed-point return sum);
+// lane 0 issues one atomic per non-zero slot.
 RLR_DEV unsigned long long warp_sum(unsigned long long x) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) x += __shfl_xor_sync(0xffffffffu, x, off);
@@ -1226,21 +1264,21 @@ RLR_DEV unsigned long long warp_sum(unsigned long long x) {
 RLR_DEV void accumulate_stats(unsigned long long* stats, bool active, const StepFlags& fl, int ep_len, double ep_ret) {
     if (stats == nullptr) return;
     const bool fin = active && fl.done;
-    unsigned long long packed = (active ? 1ull : 0ull) | ((fin ? 1ull : 0ull) << 6) | (((fin && fl.landed) ? 1ull : 0ull) << 12) |
-                                (((fin && fl.viol) ? 1ull : 0ull) << 18) | (((fin && fl.trunc) ? 1ull : 0ull) << 24) |
-                                ((active ? (unsigned long long)fl.natt : 0ull) << 30);
-    packed = warp_sum(packed);
-    const unsigned any_fin = __ballot_sync(0xffffffffu, fin);
+    // five 6-bit counters (<= 32 lanes each) in one 32-bit word and the attempt count: two REDUX instructions per step
+    const unsigned packed = (active ? 1u : 0u) | ((fin ? 1u : 0u) << 6) | (((fin && fl.landed) ? 1u : 0u) << 12) |
+                            (((fin && fl.viol) ? 1u : 0u) << 18) | (((fin && fl.trunc) ? 1u : 0u) << 24);
+    const unsigned cnt = __reduce_add_sync(0xffffffffu, packed);
+    const unsigned n_att = __reduce_add_sync(0xffffffffu, active ? (unsigned)fl.natt : 0u);
     unsigned long long len = 0ull, ret = 0ull;
-    if (any_fin) {       // warp-uniform
-        len = warp_sum(fin ? (unsigned long long)ep_len : 0ull);
+    if (cnt & (63u << 6)) {       // warp-uniform: some lane finished an episode
+        len = (unsigned long long)__reduce_add_sync(0xffffffffu, fin ? (unsigned)ep_len : 0u);
         ret = warp_sum(fin ? (unsigned long long)(long long)llrint(ep_ret * 1048576.0) : 0ull);
     }
     if ((threadIdx.x & 31) == 0) {
-        const unsigned long long n_steps = packed & 63ull, n_done = (packed >> 6) & 63ull, n_land = (packed >> 12) & 63ull;
-        const unsigned long long n_viol = (packed >> 18) & 63ull, n_trunc = (packed >> 24) & 63ull, n_att = packed >> 30;
+        const unsigned long long n_steps = cnt & 63u, n_done = (cnt >> 6) & 63u, n_land = (cnt >> 12) & 63u;
+        const unsigned long long n_viol = (cnt >> 18) & 63u, n_trunc = (cnt >> 24) & 63u;
         if (n_steps) atomicAdd(stats + RLR_STAT_STEPS, n_steps);
-        if (n_att) atomicAdd(stats + RLR_STAT_ATTEMPTS, n_att);
+        if (n_att) atomicAdd(stats + RLR_STAT_ATTEMPTS, (unsigned long long)n_att);
         if (n_done) {
             atomicAdd(stats + RLR_STAT_DONE, n_done);
             if (n_land) atomicAdd(stats + RLR_STAT_LANDED, n_land);
@@ -1252,17 +1290,13 @@ RLR_DEV void accumulate_stats(unsigned long long* stats, bool active, const Step
     }
 }
 
-// finished-episode handling shared by step and rollout kernels: record episode info, then reset in registers
+// finished-episode handling shared by step and rollout kernels: reset in registers from an injected or a warp-sampled IC
 template <class S>
-RLR_DEV void finish_and_reset(const RlrParams& p, EnvState<S>& st, const float* ic_inject, int64_t i, int64_t env_offset, uint64_t seed,
-                              float (&obs)[S::N]) {
+RLR_DEV void finish_and_reset(const RlrParams& p, EnvState<S>& st, const float* ic_inject, int64_t i, float (&ic)[S::N], float (&obs)[S::N]) {
     st.episode += 1;
-    float ic[S::N];
     if (ic_inject != nullptr) {
 #pragma unroll
         for (int c = 0; c < S::N; ++c) ic[c] = ic_inject[i * S::N + c];
-    } else {
-        sample_ic<S::N>(p, seed, env_offset + i, st.episode, ic);
     }
     reset_from_ic<S>(p, ic, st.y, st.v0, obs);
     st.k = 0;
@@ -1278,13 +1312,14 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
     StepFlags fl = {0, 0, 0, 0, 0, 0};
     int ep_len = 0;
     double ep_ret = 0.0;
+    EnvState<S> st;
+    st.episode = 0;
+    float obs[S::N];
     RLR_PHASE(-1);
     if (active) {
-        EnvState<S> st;
         load_state<S>(gs, n, i, st);
         float u[3], a_thr;
         map_action<S>(p, actions, action_kind, i, u, a_thr);
-        float obs[S::N];
         StepRes res;
         RLR_PHASE(0);                   // 0: state / action loads
         env_step<S>(p, st, u, a_thr, obs, res, fl, sK);
@@ -1310,8 +1345,14 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
             if (out.terminal_obs) write_obs<S>(p, out.terminal_obs, i, obs);
             if (out.fin_ret) out.fin_ret[i] = st.ep_ret;
             if (out.fin_len) out.fin_len[i] = st.k;
-            finish_and_reset<S>(p, st, ic_inject, i, env_offset, seed, obs);
         }
+    }
+    // ---- auto-reset: the finished lanes' initial conditions are sampled by the whole warp (sample_ic_warp)
+    float ic[S::N];
+    const bool finished = active && fl.done;
+    if (ic_inject == nullptr) sample_ic_warp<S::N>(p, seed, env_offset + i, st.episode + 1, finished, ic);
+    if (active) {
+        if (finished) finish_and_reset<S>(p, st, ic_inject, i, ic, obs);
         RLR_PHASE(6);                   // 6: auto-reset
         write_obs<S>(p, out.obs, i, obs);
         store_state<S>(gs, n, i, st);
@@ -1350,6 +1391,7 @@ __global__ void RLR_KERNEL_BOUNDS(S) rollout_kernel(const __grid_constant__ RlrP
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n;
     EnvState<S> st;
+    st.episode = 0;
     if (active) load_state<S>(gs, n, i, st);
     const int na = (p.dof == 1) ? 1 : S::NA;
     const int no = (p.dof == 1) ? 2 : S::NOBS;
@@ -1367,11 +1409,16 @@ __global__ void RLR_KERNEL_BOUNDS(S) rollout_kernel(const __grid_constant__ RlrP
             StepRes res;
             env_step<S>(p, st, u, a_thr, obs, res, fl, sK);
             ep_len = st.k; ep_ret = st.ep_ret;
-            if (fl.done) finish_and_reset<S>(p, st, nullptr, i, env_offset, seed, obs);
-            if (obs_buf) write_obs<S>(p, obs_buf + (int64_t)t * n * no, i, obs);
             if (reward_buf) reward_buf[(int64_t)t * n + i] = (float)res.reward;
             if (done_buf) done_buf[(int64_t)t * n + i] = (uint8_t)fl.done;
             if (trunc_buf) trunc_buf[(int64_t)t * n + i] = (uint8_t)fl.trunc;
+        }
+        float ic[S::N];
+        const bool finished = active && fl.done;
+        sample_ic_warp<S::N>(p, seed, env_offset + i, st.episode + 1, finished, ic);
+        if (active) {
+            if (finished) finish_and_reset<S>(p, st, nullptr, i, ic, obs);
+            if (obs_buf) write_obs<S>(p, obs_buf + (int64_t)t * n * no, i, obs);
         }
         accumulate_stats(stats, active, fl, ep_len, ep_ret);
     }
