@@ -25,6 +25,7 @@ ENVS_PER_GPU = 65536
 PREP_STEPS = 150            # untimed state preparation: desynchronise episodes so resets/events occur at their steady rate
 FLOP_STEP, FLOP_ATTEMPT = 540, 1530      # algorithmic fp64 flop per 6DOF env step: 540 + 1530*k
 BYTES_STEP = 320                          # algorithmic HBM bytes per env step when state round-trips
+TRAFFIC_BYTES_PER_LAUNCH = 24.1e6         # measured DRAM read+write of one step_kernel<Sys6> launch at 65 536 envs (profiles/r01c)
 
 
 def env_config():
@@ -78,15 +79,17 @@ def run_reference(args):
     cores = os.cpu_count()
     vals = []
     farm = SP.CpuFarm(6, env_config(), 800, procs=cores)
+    # bounded: the whole --steps K --warmup W run stays under ~2 minutes of sampling whatever K and W are
+    per_step = max(0.25, min(args.ref_seconds, 110.0 / (args.warmup + args.steps)))
     for i in range(args.warmup + args.steps):
-        r = farm.sample(args.ref_seconds)
+        r = farm.sample(per_step)
         if i >= args.warmup:
             vals.append(r)
     farm.close()
     steps = sum(v["steps"] for v in vals)
     wall = sum(v["wall_s"] for v in vals)
     value = steps / wall
-    sample = f"{cores} single-env worker processes x {args.ref_seconds:.1f} s of random-action 6DOF env_config steps per bench step"
+    sample = f"{cores} single-env worker processes x {per_step:.2f} s of random-action 6DOF env_config steps per bench step"
     line = {"impl": "reference", "metric": "env_steps_per_sec_6dof", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -180,6 +183,30 @@ def run_ours(args):
         st_all = st
     value = n * world * K / (max_ms * 1e-3)
 
+    # ---- end to end through the public VecEnv API with HOST buffers (pinned): H2D of the actions + D2H of obs / reward / done inside
+    # the timed region, every step, on EVERY rank; whole-job value = all ranks' env-steps / the slowest rank's wall time
+    venv = RocketVecEnv(n, dof=6, max_episode_steps=800, device=dev, math_mode=args.math, env_offset=rank * n, **cfg)
+    venv.reset_tensor()
+    for t in range(PREP_STEPS):
+        venv.step_tensor(chunk[t])
+    Ke = min(K, 200)
+    h_actions = [actions[W + t].cpu().pin_memory() for t in range(Ke)]
+    for t in range(3):
+        venv.step_host(h_actions[t])
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(Ke):
+        venv.step_host(h_actions[t])
+    torch.cuda.synchronize(dev)
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e = n * world * Ke / float(e2e_s.item())
+    e2e_d = {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": venv.h2d_bytes_per_step() * world,
+             "d2h_bytes_per_step": venv.d2h_bytes_per_step() * world, "steps": Ke,
+             "note": "RocketVecEnv.step_host on every rank: pinned host actions in, packed obs|reward|done out (one H2D + one D2H per step); "
+                     "max wall time over ranks"}
+
     line = None
     if rank == 0:
         # ---- back-to-back (no flush) and fused-rollout variants, device-timed, for the record
@@ -210,28 +237,13 @@ def run_ours(args):
         except Exception:  # noqa: BLE001
             hbm_peak = 6650.0
         roofline = {"bound": "fp64_alu", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                    "traffic": None, "kernel": "step_kernel<Sys6>", "peak_source": "rlr_fma_peak DFMA microbench in this run "
+                    "traffic": TRAFFIC_BYTES_PER_LAUNCH if n == ENVS_PER_GPU else None,
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel<Sys6> launch, ncu --set full "
+                                      "(profiles/r01c_step_kernel_ncu.txt); algorithmic bytes per launch = 320 B x 65536 = 21.0 MB",
+                    "kernel": "step_kernel<Sys6>", "peak_source": "rlr_fma_peak DFMA microbench in this run "
                     "(MEASURED_PEAKS.json has no FP64 figure)", "flop_model": "540 + 1530*attempts per env step; attempts counted by the kernel",
                     "attempts_per_step": st["attempts"] / max(1, st["steps"]),
                     "hbm": {"achieved": hbm_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_gbs / hbm_peak, "bytes_per_env_step": BYTES_STEP}}
-        # ---- end to end through the public VecEnv API with HOST buffers (pinned), H2D + D2H inside the timed region
-        venv = RocketVecEnv(n, dof=6, max_episode_steps=800, device=dev, math_mode=args.math, **cfg)
-        venv.reset_tensor()
-        for t in range(PREP_STEPS):
-            venv.step_tensor(chunk[t])
-        Ke = min(K, 200)
-        h_actions = [actions[W + t].cpu().pin_memory() for t in range(Ke)]
-        for t in range(3):
-            venv.step_host(h_actions[t])
-        torch.cuda.synchronize(dev)
-        t0 = time.perf_counter()
-        for t in range(Ke):
-            venv.step_host(h_actions[t])
-        torch.cuda.synchronize(dev)
-        e2e = n * Ke / (time.perf_counter() - t0)
-        e2e_d = {"value": e2e * world, "unit": "env-steps/s", "h2d_bytes_per_step": venv.h2d_bytes_per_step(),
-                 "d2h_bytes_per_step": venv.d2h_bytes_per_step(), "note": "RocketVecEnv.step_host: pinned host actions in, obs/reward/done "
-                 "out; measured on rank 0 and scaled by the rank count (ranks are independent)"}
         # ---- CPU baseline: the reference's Python/scipy path (oracle port) on this box's host cores, bounded sample
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -274,8 +286,6 @@ def main():
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
-        if args.steps > 20:
-            args.steps = 20        # bounded: every reference "step" is args.ref_seconds of CPU work on all cores
         run_reference(args)
     else:
         world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -34,11 +34,12 @@ class RocketBatch:
         self.episode = torch.zeros(n, dtype=torch.int32, device=dev)
         self.v0 = torch.zeros(n, dtype=torch.float32, device=dev)
         self.ep_ret = torch.zeros(n, dtype=torch.float64, device=dev)
-        # per-step outputs
-        self.obs = torch.zeros((n, no), dtype=torch.float32, device=dev)
-        self.reward = torch.zeros(n, dtype=torch.float32, device=dev)
+        # per-step outputs.  obs | reward | done are views of ONE packed buffer so that the host-facing API needs a single D2H copy
+        self.out_pack = torch.zeros(n * no * 4 + n * 4 + n, dtype=torch.uint8, device=dev)
+        self.obs = self.out_pack[:n * no * 4].view(torch.float32).view(n, no)
+        self.reward = self.out_pack[n * no * 4:n * no * 4 + n * 4].view(torch.float32)
+        self.done = self.out_pack[n * no * 4 + n * 4:]
         self.reward64 = torch.zeros(n, dtype=torch.float64, device=dev)
-        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.truncated = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.terminal_obs = torch.zeros((n, no), dtype=torch.float32, device=dev)
         self.fin_ret = torch.zeros(n, dtype=torch.float64, device=dev)

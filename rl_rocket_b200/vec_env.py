@@ -54,9 +54,10 @@ class RocketVecEnv(_VecEnvBase):
         self._h_actions = torch.zeros((n,) if self.discrete else (n, self.spec.nact),
                                       dtype=torch.int64 if self.discrete else torch.float32).pin_memory()
         self._d_actions = torch.zeros_like(self._h_actions, device=self.device)
-        self._h_obs = torch.zeros((n, no), dtype=torch.float32).pin_memory()
-        self._h_rew = torch.zeros(n, dtype=torch.float32).pin_memory()
-        self._h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        self._h_pack = torch.zeros_like(self.batch.out_pack, device="cpu").pin_memory()      # obs | reward | done, one D2H per step
+        self._h_obs = self._h_pack[:n * no * 4].view(torch.float32).view(n, no)
+        self._h_rew = self._h_pack[n * no * 4:n * no * 4 + n * 4].view(torch.float32)
+        self._h_done = self._h_pack[n * no * 4 + n * 4:]
         self._t_start = time.time()
         self._pending = False
         self.metadata = {"render.modes": []}
@@ -79,9 +80,7 @@ class RocketVecEnv(_VecEnvBase):
         self._d_actions.copy_(actions_host.reshape(self._d_actions.shape), non_blocking=True)
         b = self.batch
         b.step_tensor(self._d_actions)
-        self._h_obs.copy_(b.obs, non_blocking=True)
-        self._h_rew.copy_(b.reward, non_blocking=True)
-        self._h_done.copy_(b.done, non_blocking=True)
+        self._h_pack.copy_(b.out_pack, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self._h_obs, self._h_rew, self._h_done
 
@@ -89,7 +88,7 @@ class RocketVecEnv(_VecEnvBase):
         return self._h_actions.numel() * self._h_actions.element_size()
 
     def d2h_bytes_per_step(self):
-        return sum(t.numel() * t.element_size() for t in (self._h_obs, self._h_rew, self._h_done))
+        return self._h_pack.numel()
 
     # ---------------------------------------------------------------- SB3 VecEnv API
     def reset(self):
