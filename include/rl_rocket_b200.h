@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define RLR_ABI_VERSION 1
+#define RLR_ABI_VERSION 2
 #define RLR_NMAX 14          /* state components: 14 (6DOF), 7 (3DOF / 1DOF) */
 #define RLR_MAX_DISCRETE 16
 
@@ -101,6 +101,8 @@ typedef struct RlrStepOut {
     int32_t* natt;           /* [n] RK45 attempts spent in this step (nfev = 2 + 6*natt) */
     void*    y_pre_reset;    /* [ndim][n] state after the step, before auto-reset (same dtype as y) */
     double*  reward_terms;   /* [6][n] velocity_tracking, thrust_penalty, eta, attitude_constraint, attitude_hint, rew_goal */
+    double*  vtarg;          /* [4][n] target velocity (3 components; 2 for 3DOF, third = 0) and t_go of _compute_vtarg
+                                (rocket_env.py:986-1014 / :215-247) -- what the reference appends to vtarg_history */
     unsigned long long* stats; /* [RLR_NSTATS] device accumulators, atomically added (see below) */
 } RlrStepOut;
 

@@ -11,6 +11,7 @@ MAX_DISCRETE = 16
 NSTATS = 8
 STAT_NAMES = ("steps", "attempts", "done", "landed", "viol", "trunc", "len_sum", "ret_sum_fx")
 
+ABI_VERSION = 2
 ACT_NORMALIZED, ACT_PHYSICAL, ACT_DISCRETE = 0, 1, 2
 MATH_EXACT, MATH_FAST = 0, 1
 F64, F32 = 0, 1
@@ -42,7 +43,7 @@ class RlrState(C.Structure):
 
 class RlrStepOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("obs", "reward", "reward64", "done", "truncated", "terminal_obs", "fin_ret", "fin_len",
-                                           "flags", "natt", "y_pre_reset", "reward_terms", "stats")]
+                                           "flags", "natt", "y_pre_reset", "reward_terms", "vtarg", "stats")]
 
 
 EXPORTS = ("rlr_abi_version", "rlr_last_error", "rlr_sizeof_params", "rlr_ndim", "rlr_nact", "rlr_nobs",
@@ -64,7 +65,7 @@ def load():
         if not hasattr(lib, name):
             raise RuntimeError(f"{LIB_PATH} does not export {name}")
     lib.rlr_last_error.restype = C.c_char_p
-    if lib.rlr_abi_version() != 1:
+    if lib.rlr_abi_version() != ABI_VERSION:
         raise RuntimeError("librlrocket.so ABI version mismatch")
     if lib.rlr_sizeof_params() != C.sizeof(RlrParams):
         raise RuntimeError("RlrParams layout mismatch between Python and librlrocket.so")

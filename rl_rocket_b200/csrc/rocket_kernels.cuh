@@ -1015,6 +1015,7 @@ RLR_DEV void reset_from_ic(const RlrParams& p, float (&ic)[S::N], double (&y)[S:
 struct StepRes {
     double reward;
     double terms[6];
+    double vt[4];            // target velocity (3) and t_go of _compute_vtarg
     int viol, landed, status, done;
 };
 
@@ -1037,15 +1038,13 @@ RLR_DEV void reward6(const RlrParams& p, const float (&s)[14], const float* u, f
     const double fac = 1 - exp(RLR_DIV(-t_go, tau));
     const double mv0 = (double)(-v0);
 #if RLR_EXACT
-    const double d0 = (double)s[3] - (mv0 * (rh0 / den)) * fac;
-    const double d1 = (double)s[4] - (mv0 * (rh1 / den)) * fac;
-    const double d2 = (double)s[5] - (mv0 * (rh2 / den)) * fac;
+    const double vt0 = (mv0 * (rh0 / den)) * fac, vt1 = (mv0 * (rh1 / den)) * fac, vt2 = (mv0 * (rh2 / den)) * fac;
 #else
     const double iden = rcp_(den);
-    const double d0 = (double)s[3] - (mv0 * (rh0 * iden)) * fac;
-    const double d1 = (double)s[4] - (mv0 * (rh1 * iden)) * fac;
-    const double d2 = (double)s[5] - (mv0 * (rh2 * iden)) * fac;
+    const double vt0 = (mv0 * (rh0 * iden)) * fac, vt1 = (mv0 * (rh1 * iden)) * fac, vt2 = (mv0 * (rh2 * iden)) * fac;
 #endif
+    const double d0 = (double)s[3] - vt0, d1 = (double)s[4] - vt1, d2 = (double)s[5] - vt2;
+    o.vt[0] = vt0; o.vt[1] = vt1; o.vt[2] = vt2; o.vt[3] = t_go;
     // Rotation.from_quat(roll(q_f32,-1)).as_euler("zyx")
     const double q0 = s[6], q1 = s[7], q2 = s[8], q3 = s[9];
 #if RLR_EXACT
@@ -1114,8 +1113,9 @@ RLR_DEV void reward3(const RlrParams& p, const float (&s)[7], const float* u, fl
     const double den = py_max(1e-3, nr);
     const double fac = 1 - exp(-t_go / tau);
     const double mv0 = (double)(-v0);
-    const double d0 = (double)s[3] - (mv0 * (rh0 / den)) * fac;
-    const double d1 = (double)s[4] - (mv0 * (rh1 / den)) * fac;
+    const double vt0 = (mv0 * (rh0 / den)) * fac, vt1 = (mv0 * (rh1 / den)) * fac;
+    const double d0 = (double)s[3] - vt0, d1 = (double)s[4] - vt1;
+    o.vt[0] = vt0; o.vt[1] = vt1; o.vt[2] = 0.0; o.vt[3] = t_go;
     const float zeta = fadd(s[2], -1.5707963267948966f);
     const float az = fabsf(zeta);
     const float rn = f32_norm2(s[0], s[1]), vn = f32_norm2(s[3], s[4]);
@@ -1339,6 +1339,10 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
             double* yp = (double*)out.y_pre_reset;
 #pragma unroll
             for (int c = 0; c < S::N; ++c) yp[c * n + i] = st.y[c];
+        }
+        if (out.vtarg) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) out.vtarg[c * n + i] = res.vt[c];
         }
         RLR_PHASE(5);                   // 5: per-step output stores
         if (fl.done) {

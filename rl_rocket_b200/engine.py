@@ -50,12 +50,13 @@ class RocketBatch:
         self.natt = torch.zeros(n, dtype=torch.int32, device=dev) if self.debug else None
         self.y_pre_reset = torch.zeros((nd, n), dtype=torch.float64, device=dev) if self.debug else None
         self.reward_terms = torch.zeros((6, n), dtype=torch.float64, device=dev) if self.debug else None
+        self.vtarg = torch.zeros((4, n), dtype=torch.float64, device=dev) if self.debug else None
         self.launches = 0
         # the buffers above are persistent, so the pointer structs handed to the C ABI are built once
         self._st = N.RlrState(_ptr(self.y), _ptr(self.k), _ptr(self.episode), _ptr(self.v0), _ptr(self.ep_ret))
         self._ot = N.RlrStepOut(_ptr(self.obs), _ptr(self.reward), _ptr(self.reward64), _ptr(self.done), _ptr(self.truncated),
                                 _ptr(self.terminal_obs), _ptr(self.fin_ret), _ptr(self.fin_len), _ptr(self.flags), _ptr(self.natt),
-                                _ptr(self.y_pre_reset), _ptr(self.reward_terms), _ptr(self.stats))
+                                _ptr(self.y_pre_reset), _ptr(self.reward_terms), _ptr(self.vtarg), _ptr(self.stats))
         self._dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._act_shape = (n, spec.nact)
         self._step_fn = self.lib.rlr_step

@@ -80,6 +80,8 @@ class _SingleEnv(spaces.GymEnv):
         flags = int(b.flags[0].item())
         reward = float(b.reward64[0].item())
         terms = b.reward_terms[:, 0].cpu().numpy()
+        nv = 3 if self._dof == 6 else 2
+        self.vtarg_history.append(b.vtarg[:nv, 0].cpu().numpy())      # rocket_env.py:245 / :1012
         if done:    # undo the fused auto-reset: restore the terminal state so that further step() calls behave like the reference
             b.y[:, 0] = b.y_pre_reset[:, 0]
             b.k.copy_(k_prev + 1)

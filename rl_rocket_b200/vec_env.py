@@ -39,11 +39,13 @@ class _LazyInfos(list):
 
 class RocketVecEnv(_VecEnvBase):
     def __init__(self, num_envs, dof=6, max_episode_steps=None, device="cuda:0", discrete_actions=False, discrete_table=None,
-                 reward_annealing=False, math_mode="fast", env_offset=0, **env_kwargs):
+                 reward_annealing=False, math_mode="fast", env_offset=0, trace_indices=None, trace_capacity=4096, **env_kwargs):
         table = (discrete_table or DEFAULT_DISCRETE_TABLE) if discrete_actions else None
         self.spec = EnvSpec(dof, max_episode_steps=max_episode_steps or 0, reward_mode=1 if reward_annealing else 0,
                             discrete_table=table, **env_kwargs)
-        self.batch = RocketBatch(self.spec, num_envs, device=device, math_mode=math_mode, env_offset=env_offset)
+        self.batch = RocketBatch(self.spec, num_envs, device=device, math_mode=math_mode, env_offset=env_offset,
+                                 debug_outputs=trace_indices is not None)
+        self.trace = TrajectoryTrace(self.batch, trace_indices, trace_capacity) if trace_indices is not None else None
         obs_space = spaces.Box(low=-1, high=1, shape=(self.spec.nobs,))
         act_space = spaces.Discrete(len(table)) if discrete_actions else spaces.Box(low=-1, high=1, shape=(self.spec.nact,))
         super().__init__(num_envs, obs_space, act_space)
@@ -64,10 +66,16 @@ class RocketVecEnv(_VecEnvBase):
 
     # ---------------------------------------------------------------- tensor-native fast path
     def reset_tensor(self):
-        return self.batch.reset()
+        obs = self.batch.reset()
+        if self.trace is not None:
+            self.trace.start()
+        return obs
 
     def step_tensor(self, actions):
-        return self.batch.step_tensor(actions)
+        out = self.batch.step_tensor(actions)
+        if self.trace is not None:
+            self.trace.record(actions)
+        return out
 
     def rollout_tensor(self, actions, obs_buf=None, reward_buf=None, done_buf=None, trunc_buf=None):
         return self.batch.rollout(actions, obs_buf, reward_buf, done_buf, trunc_buf)
@@ -79,7 +87,7 @@ class RocketVecEnv(_VecEnvBase):
             actions_host = torch.as_tensor(np.ascontiguousarray(actions_host))
         self._d_actions.copy_(actions_host.reshape(self._d_actions.shape), non_blocking=True)
         b = self.batch
-        b.step_tensor(self._d_actions)
+        self.step_tensor(self._d_actions)
         self._h_pack.copy_(b.out_pack, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self._h_obs, self._h_rew, self._h_done
@@ -92,8 +100,7 @@ class RocketVecEnv(_VecEnvBase):
 
     # ---------------------------------------------------------------- SB3 VecEnv API
     def reset(self):
-        obs = self.batch.reset()
-        return obs.cpu().numpy()
+        return self.reset_tensor().cpu().numpy()
 
     def step_async(self, actions):
         a = np.asarray(actions)
@@ -174,3 +181,100 @@ class RocketVecEnv(_VecEnvBase):
 
 
 _EMPTY_INFO = {}
+
+
+class TrajectoryTrace:
+    """Device-side trajectory history of a few selected environments of a batch -- the vectorised counterpart of what the
+    reference keeps per environment in `SIM.states / SIM.actions / SIM.times` and `vtarg_history` (simulator.py:28-31, :201-206,
+    :246-248; rocket_env.py:245, :1012) and reads back through `states_to_dataframe`, `actions_to_dataframe`, `vtarg_to_dataframe`
+    and `used_mass` (rocket_env.py:1016-1034) for EpisodeAnalyzer / RecordVideoFigure (wrappers.py:189-235).
+
+    Nothing is added to the step kernel's hot path beyond the optional `y_pre_reset` / `vtarg` outputs: after every step the m
+    selected columns are gathered into ring buffers `[capacity, m, ...]` on the device (no host synchronisation); the host reads
+    them only when an analysis asks for a dataframe.  Row 0 of an episode is its initial condition (action 0, as simulator.py:30).
+    """
+
+    def __init__(self, batch, indices, capacity=4096):
+        self.batch = batch
+        self.idx = torch.as_tensor(list(indices), dtype=torch.long, device=batch.device)
+        if self.idx.numel() == 0 or int(self.idx.min()) < 0 or int(self.idx.max()) >= batch.n:
+            raise ValueError("trace_indices must be non-empty environment indices of this batch")
+        m, nd, na, dev = self.idx.numel(), batch.spec.ndim, batch.spec.nact, batch.device
+        self.capacity = int(capacity)
+        self.states = torch.zeros((self.capacity, m, nd), dtype=torch.float64, device=dev)
+        self.actions = torch.zeros((self.capacity, m, na), dtype=torch.float32, device=dev)
+        self.post = torch.zeros((self.capacity, m, nd), dtype=torch.float64, device=dev)      # state after auto-reset (next episode's IC)
+        self.vtarg = torch.zeros((self.capacity, m, 4), dtype=torch.float64, device=dev)
+        self.reward = torch.zeros((self.capacity, m), dtype=torch.float64, device=dev)
+        self.step_in_episode = torch.zeros((self.capacity, m), dtype=torch.int32, device=dev)      # 0 = initial condition row
+        self.episode = torch.zeros((self.capacity, m), dtype=torch.int32, device=dev)
+        self.count = 0            # rows written so far (monotonic; row r lives at r % capacity)
+
+    def _put(self, states, actions, vtarg, reward, k, episode):
+        r = self.count % self.capacity
+        self.states[r].copy_(states)
+        self.post[r].copy_(self.batch.y[:, self.idx].T)
+        self.actions[r].copy_(actions)
+        self.vtarg[r].copy_(vtarg)
+        self.reward[r].copy_(reward)
+        self.step_in_episode[r].copy_(k)
+        self.episode[r].copy_(episode)
+        self.count += 1
+
+    def start(self):
+        """Called after a reset of the whole batch: row 0 = the initial conditions."""
+        b, m = self.batch, self.idx.numel()
+        self.count = 0
+        z = torch.zeros((m,), dtype=torch.float64, device=b.device)
+        self._put(b.y[:, self.idx].T, torch.zeros((m, b.spec.nact), device=b.device), torch.zeros((m, 4), dtype=torch.float64, device=b.device),
+                  z, torch.zeros((m,), dtype=torch.int32, device=b.device), b.episode[self.idx])
+
+    def record(self, actions):
+        """Called after every step: the post-step (pre-reset) state, the action taken, vtarg / t_go, the reward, and the state after
+        the fused auto-reset (`post`), which is the next episode's initial condition for the environments that just finished."""
+        b, idx = self.batch, self.idx
+        a = actions[idx].to(torch.float32).reshape(idx.numel(), -1)
+        done = b.done[idx].bool()
+        # k was already reset for finished environments: their last step index comes from fin_len
+        k = torch.where(done, b.fin_len[idx], b.k[idx])
+        ep = b.episode[idx] - done.to(torch.int32)
+        self._put(b.y_pre_reset[:, idx].T, a, b.vtarg[:, idx].T, b.reward64[idx], k, ep)
+
+    def to_host(self):
+        """dict of numpy arrays in chronological order (the last `capacity` rows)."""
+        n = min(self.count, self.capacity)
+        order = [(self.count - n + j) % self.capacity for j in range(n)]
+        sel = torch.as_tensor(order, dtype=torch.long, device=self.batch.device)
+        return {name: getattr(self, name)[sel].cpu().numpy()
+                for name in ("states", "post", "actions", "vtarg", "reward", "step_in_episode", "episode")}
+
+    def last_episode(self, j=0):
+        """Rows of the most recent (possibly running) episode of traced environment j: (states, actions, vtarg, times)."""
+        h = self.to_host()
+        ep = h["episode"][:, j]
+        rows = np.nonzero(ep == ep[-1])[0]
+        states, actions, vtarg, k = h["states"][rows, j], h["actions"][rows, j], h["vtarg"][rows, j], h["step_in_episode"][rows, j]
+        if k[0] != 0 and rows[0] > 0:          # the episode began with an auto-reset: its IC is the `post` state of the previous row
+            states = np.concatenate([h["post"][rows[0] - 1, j][None], states])
+            actions = np.concatenate([np.zeros_like(actions[:1]), actions])
+            vtarg = np.concatenate([np.zeros_like(vtarg[:1]), vtarg])
+            k = np.concatenate([[0], k])
+        t = k.astype(np.float64) * self.batch.spec.timestep
+        return states, actions, vtarg, np.round(t, 3)
+
+    def states_to_dataframe(self, j=0, names=None):
+        import pandas as pd
+        return pd.DataFrame(self.last_episode(j)[0], columns=names)
+
+    def actions_to_dataframe(self, j=0, names=None):
+        import pandas as pd
+        return pd.DataFrame(self.last_episode(j)[1], columns=names)
+
+    def vtarg_to_dataframe(self, j=0):
+        import pandas as pd
+        nv = 3 if self.batch.spec.dof == 6 else 2
+        return pd.DataFrame(self.last_episode(j)[2][1:, :nv], columns=["v_x", "v_y", "v_z"][:nv])
+
+    def used_mass(self, j=0):
+        s = self.last_episode(j)[0]
+        return s[0, -1] - s[-1, -1]

@@ -173,3 +173,71 @@ def test_config5_sb3_style_rollout_collection():
         obs = new_obs
     assert len(ep_info) >= N * (n_steps // tl) - N and n_boot > 0
     assert np.isfinite(buf_obs).all() and np.isfinite(buf_rew).all()
+
+
+def test_trajectory_trace_matches_oracle_history():
+    """device-side trace of selected environments = what the reference keeps in SIM.states / actions / times and
+    vtarg_history, here checked against the oracle's per-step states and vtarg for the traced columns, across auto-resets."""
+    from oracle import c_oracle as O
+    from rl_rocket_b200.vec_env import RocketVecEnv
+    N, T, tl = 128, 90, 30
+    cfg = G.cfg6()
+    idx = [3, 64, 127]
+    venv = RocketVecEnv(N, dof=6, max_episode_steps=tl, math_mode="exact", trace_indices=idx, trace_capacity=256, **cfg)
+    venv.seed(11)
+    p = O.make_params(6, max_episode_steps=tl, **cfg)
+    vec = O.VecOracle(p, N, seed=11)
+    venv.reset(); vec.reset()
+    ic0 = vec.y[:, idx].T.copy()
+    rng = np.random.RandomState(2)
+    hist_y, hist_a = [], []
+    for t in range(T):
+        a = rng.uniform(-1, 1, (N, 3)).astype(np.float32)
+        venv.step_tensor(torch.as_tensor(a).cuda())
+        out = vec.step(a)
+        hist_y.append(out["y_pre_reset"][:, idx].T.copy()); hist_a.append(a[idx])
+    h = venv.trace.to_host()
+    assert h["states"].shape == (T + 1, 3, 14)
+    assert np.array_equal(h["states"][0], ic0)
+    norm = venv.spec.state_normalizer
+    assert (np.abs(h["states"][1:] - np.array(hist_y)) / norm).max() <= G.STATE_TOL
+    assert np.array_equal(h["actions"][1:], np.array(hist_a))
+    # the last (running) episode of every traced env starts at an initial condition (k == 0) and has consecutive times
+    for j in range(3):
+        s, a, vt, times = venv.trace.last_episode(j)
+        assert times[0] == 0.0 and np.allclose(np.diff(times), cfg["timestep"])
+        assert len(s) == len(a) == len(vt) == len(times) and len(s) <= tl + 1
+        assert np.array_equal(s[0].astype(np.float32).astype(np.float64), s[0])          # an IC: f32-valued state
+        assert abs(venv.trace.used_mass(j) - (s[0, -1] - s[-1, -1])) == 0
+        assert list(venv.trace.vtarg_to_dataframe(j).columns) == ["v_x", "v_y", "v_z"]
+    # vtarg of the traced rows against the scalar oracle's _compute_vtarg on the same f32 states
+    env = O.ScalarEnv(p)
+    s_last, a_last, vt_last, _ = venv.trace.last_episode(0)
+    if len(s_last) > 1:
+        env.reset(s_last[0].astype(np.float32))
+        for r in range(1, len(s_last)):
+            _, _, _, info = env.step(a_last[r])
+            assert np.abs(info["vtarg"] - vt_last[r, :3]).max() <= 1e-9 * max(1.0, np.abs(info["vtarg"]).max())
+            assert abs(info["t_go"] - vt_last[r, 3]) <= 1e-9 * max(1.0, abs(info["t_go"]))
+
+
+def test_facade_vtarg_history_matches_oracle():
+    """Rocket6DOF.vtarg_history / vtarg_to_dataframe (rocket_env.py:1012, :1026-1029) against the oracle on the KAT-2 replay."""
+    from oracle import c_oracle as O
+    from rl_rocket_b200.envs import Rocket6DOF
+    cfg = G.cfg6()
+    cfg["IC"] = [500, 100, 100, -50, 0, 0, 1, 0, 0, 0, 0, 0, 0, 45e3]
+    cfg["ICRange"] = [0] * 14
+    env = Rocket6DOF(**cfg)
+    ref = O.ScalarEnv(O.make_params(6, **cfg))
+    env.reset(); ref.reset(np.float32(cfg["IC"]))
+    for t in range(40):
+        a = np.float32([0.3, -0.2, 0.5])
+        _, _, done, _ = env.step(a)
+        _, _, rdone, info = ref.step(a)
+        assert done == rdone
+        assert np.abs(env.vtarg_history[-1] - info["vtarg"]).max() <= 1e-9 * max(1.0, np.abs(info["vtarg"]).max())
+        if done:
+            break
+    df = env.vtarg_to_dataframe()
+    assert df.shape == (len(env.vtarg_history), 3)
