@@ -225,6 +225,25 @@ def run_ours(args):
         e1.record()
         e1.synchronize()
         fused = n * Tr / (e0.elapsed_time(e1) * 1e-3)
+        # ---- RLR_F32 precision (binary32 state, tolerance 1e-4, tests/test_gpu_f32.py) of the same workload, for the record
+        env32 = RocketBatch(spec, n, device=dev, seed=42, env_offset=rank * n, math_mode="fast", precision="f32")
+        env32.reset()
+        for t in range(PREP_STEPS):
+            env32.step_tensor(chunk[t])
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for t in range(K):
+            env32.step_tensor(actions[W + t])
+        e1.record()
+        e1.synchronize()
+        f32_b2b = n * K / (e0.elapsed_time(e1) * 1e-3)
+        env32.rollout(actions[W:W + 3])
+        e0.record()
+        env32.rollout(actions[W:W + Tr])
+        e1.record()
+        e1.synchronize()
+        f32_fused = n * Tr / (e0.elapsed_time(e1) * 1e-3)
+        del env32
         # ---- roofline of the dominant kernel (step_kernel<Sys6>): FP64 ALU bound, peak measured in this run
         peak = fma_peak("f64", device=dev)
         flops = FLOP_STEP * st["steps"] + FLOP_ATTEMPT * st["attempts"]
@@ -262,7 +281,8 @@ def run_ours(args):
                            "collective": "all_gather of the 64-byte episode-statistics record per rank (NCCL), timed" if world > 1 else None},
                 "clocks": clocks, "e2e": e2e_d, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "episodes_finished": st_all["done"], "wall_ms_timed_region": wall_ms,
-                "variants": {"back_to_back_no_flush": b2b, "fused_rollout_kernel": fused, "unit": "env-steps/s (rank 0 only)"}}
+                "variants": {"back_to_back_no_flush": b2b, "fused_rollout_kernel": fused, "f32_state_back_to_back": f32_b2b,
+                             "f32_state_fused_rollout": f32_fused, "unit": "env-steps/s (rank 0 only)"}}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -16,6 +16,13 @@
 RLR_DECLARE_LAUNCHERS(rlr_exact)
 RLR_DECLARE_LAUNCHERS(rlr_fast)
 
+namespace rlr_fast {      // RLR_F32 precision (6DOF, fast math only)
+int launch_step_f32(const RlrParams*, RlrState, const void*, int, const float*, RlrStepOut, int64_t, int64_t, uint64_t, cudaStream_t);
+int launch_reset_f32(const RlrParams*, RlrState, const uint8_t*, const float*, float*, int64_t, int64_t, uint64_t, cudaStream_t);
+int launch_rollout_f32(const RlrParams*, RlrState, const void*, int, int, float*, float*, uint8_t*, uint8_t*, float*, unsigned long long*,
+                       int64_t, int64_t, uint64_t, cudaStream_t);
+}
+
 namespace rlr_peak {
 int launch_fma_peak(int precision, int blocks, int threads, int iters, double* sink, double* flops_out, cudaStream_t stream);
 }
@@ -36,6 +43,13 @@ static int check_params(const RlrParams* p) {
     if (p->dof != 6 && p->dof != 3 && p->dof != 1) return fail(RLR_E_INVALID, "dof must be 6, 3 or 1");
     if (p->dt_ms <= 0 || !(p->dt > 0)) return fail(RLR_E_INVALID, "timestep must be a positive whole number of milliseconds");
     if (p->n_discrete < 0 || p->n_discrete > RLR_MAX_DISCRETE) return fail(RLR_E_INVALID, "n_discrete out of range");
+    return RLR_OK;
+}
+static int check_precision(const RlrParams* p, int precision, int math_mode) {
+    if (precision == RLR_F64) return RLR_OK;
+    if (precision != RLR_F32) return fail(RLR_E_INVALID, "bad precision");
+    if (p->dof != 6) return fail(RLR_E_UNSUPPORTED, "RLR_F32 state is implemented for the 6DOF environment only");
+    if (math_mode != RLR_MATH_FAST) return fail(RLR_E_UNSUPPORTED, "RLR_F32 state needs RLR_MATH_FAST (the exact build is the op-for-op fp64 reference)");
     return RLR_OK;
 }
 static int check_state(const RlrState& st) {
@@ -59,7 +73,8 @@ int rlr_reset(const RlrParams* p, int precision, RlrState st, const uint8_t* mas
     if (n < 0) return fail(RLR_E_INVALID, "n < 0");
     if (n == 0) return RLR_OK;            /* empty batch: nothing to do (zero-size buffers may be NULL) */
     if ((rc = check_state(st))) return rc;
-    if (precision != RLR_F64) return fail(RLR_E_UNSUPPORTED, "only RLR_F64 state is implemented");
+    if ((rc = check_precision(p, precision, RLR_MATH_FAST))) return rc;
+    if (precision == RLR_F32) return cuda_status(rlr_fast::launch_reset_f32(p, st, mask, ic_inject, obs, n, env_offset, seed, (cudaStream_t)stream));
     return cuda_status(rlr_exact::launch_reset(p, st, mask, ic_inject, obs, n, env_offset, seed, (cudaStream_t)stream));
 }
 
@@ -70,12 +85,13 @@ int rlr_step(const RlrParams* p, int precision, int math_mode, RlrState st, cons
     if (n < 0) return fail(RLR_E_INVALID, "n < 0");
     if (n == 0) return RLR_OK;
     if ((rc = check_state(st))) return rc;
-    if (precision != RLR_F64) return fail(RLR_E_UNSUPPORTED, "only RLR_F64 state is implemented");
+    if ((rc = check_precision(p, precision, math_mode))) return rc;
     if (!actions || !out.obs || !out.done) return fail(RLR_E_INVALID, "actions, out.obs and out.done are required");
     if (action_kind < 0 || action_kind > 2) return fail(RLR_E_INVALID, "bad action_kind");
     if (action_kind == RLR_ACT_DISCRETE && (p->dof != 3 || p->n_discrete <= 0))
         return fail(RLR_E_INVALID, "discrete actions need dof == 3 and a discrete_table");
     cudaStream_t s = (cudaStream_t)stream;
+    if (precision == RLR_F32) return cuda_status(rlr_fast::launch_step_f32(p, st, actions, action_kind, ic_inject, out, n, env_offset, seed, s));
     if (math_mode == RLR_MATH_EXACT) return cuda_status(rlr_exact::launch_step(p, st, actions, action_kind, ic_inject, out, n, env_offset, seed, s));
     if (math_mode == RLR_MATH_FAST) return cuda_status(rlr_fast::launch_step(p, st, actions, action_kind, ic_inject, out, n, env_offset, seed, s));
     return fail(RLR_E_INVALID, "bad math_mode");
@@ -89,12 +105,15 @@ int rlr_rollout(const RlrParams* p, int precision, int math_mode, RlrState st, c
     if (n < 0 || T < 0) return fail(RLR_E_INVALID, "n < 0 or T < 0");
     if (n == 0 || T == 0) return RLR_OK;
     if ((rc = check_state(st))) return rc;
-    if (precision != RLR_F64) return fail(RLR_E_UNSUPPORTED, "only RLR_F64 state is implemented");
+    if ((rc = check_precision(p, precision, math_mode))) return rc;
     if (!actions) return fail(RLR_E_INVALID, "actions is NULL");
     if (action_kind < 0 || action_kind > 2) return fail(RLR_E_INVALID, "bad action_kind");
     if (action_kind == RLR_ACT_DISCRETE && (p->dof != 3 || p->n_discrete <= 0))
         return fail(RLR_E_INVALID, "discrete actions need dof == 3 and a discrete_table");
     cudaStream_t s = (cudaStream_t)stream;
+    if (precision == RLR_F32)
+        return cuda_status(rlr_fast::launch_rollout_f32(p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf, trunc_buf, last_obs, stats, n,
+                                                        env_offset, seed, s));
     if (math_mode == RLR_MATH_EXACT)
         return cuda_status(rlr_exact::launch_rollout(p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf, trunc_buf, last_obs, stats, n,
                                                      env_offset, seed, s));

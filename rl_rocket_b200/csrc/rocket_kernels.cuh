@@ -1439,6 +1439,10 @@ __global__ void RLR_KERNEL_BOUNDS(S) rollout_kernel(const __grid_constant__ RlrP
 #include "experimental/rocket_pair6.cuh"
 #endif
 
+#if !RLR_EXACT
+#include "rocket_f32.cuh"           // RLR_F32 precision of the 6DOF path (fast build only)
+#endif
+
 // ------------------------------------------------------------------ host launchers (called from abi.cu)
 // Launch geometry.  6DOF: 64-thread blocks, 30 KB of dynamic shared memory each (stage matrix).  The number of co-resident
 // blocks per SM comes from the occupancy calculator; when the grid would end in a nearly empty last wave, residency is
@@ -1543,5 +1547,28 @@ int launch_rollout(const RlrParams* p, RlrState st, const void* actions, int act
     }
     return (int)cudaGetLastError();
 }
+
+#if !RLR_EXACT
+// RLR_F32 precision (6DOF only): 128-thread blocks, 27 KB of dynamic shared memory for the binary32 stage matrix
+int launch_step_f32(const RlrParams* p, RlrState st, const void* actions, int action_kind, const float* ic_inject, RlrStepOut out, int64_t n,
+                    int64_t env_offset, uint64_t seed, cudaStream_t stream) {
+    f32::step_kernel_f32<<<grid_for(n, f32::BSF), f32::BSF, f32::SMEMF_BYTES, stream>>>(*p, st, (const float*)actions, action_kind, ic_inject, out,
+                                                                                         n, env_offset, seed);
+    return (int)cudaGetLastError();
+}
+int launch_reset_f32(const RlrParams* p, RlrState st, const uint8_t* mask, const float* ic_inject, float* obs, int64_t n, int64_t env_offset,
+                     uint64_t seed, cudaStream_t stream) {
+    f32::reset_kernel_f32<<<grid_for(n, 128), 128, 0, stream>>>(*p, st, mask, ic_inject, obs, n, env_offset, seed);
+    return (int)cudaGetLastError();
+}
+int launch_rollout_f32(const RlrParams* p, RlrState st, const void* actions, int action_kind, int T, float* obs_buf, float* reward_buf,
+                       uint8_t* done_buf, uint8_t* trunc_buf, float* last_obs, unsigned long long* stats, int64_t n, int64_t env_offset,
+                       uint64_t seed, cudaStream_t stream) {
+    f32::rollout_kernel_f32<<<grid_for(n, f32::BSF), f32::BSF, f32::SMEMF_BYTES, stream>>>(*p, st, (const float*)actions, action_kind, T, obs_buf,
+                                                                                            reward_buf, done_buf, trunc_buf, last_obs, stats, n,
+                                                                                            env_offset, seed);
+    return (int)cudaGetLastError();
+}
+#endif
 
 }  // namespace RLR_NS

@@ -17,7 +17,8 @@ def _ptr(t):
 
 
 class RocketBatch:
-    def __init__(self, spec: EnvSpec, num_envs: int, device="cuda:0", seed=None, env_offset=0, math_mode="fast", debug_outputs=False):
+    def __init__(self, spec: EnvSpec, num_envs: int, device="cuda:0", seed=None, env_offset=0, math_mode="fast", debug_outputs=False,
+                 precision="f64"):
         self.lib = N.load()                      # raises if the CUDA extension is not built
         if not torch.cuda.is_available():
             raise RuntimeError("rl_rocket_b200 needs a CUDA device (there is no CPU fallback)")
@@ -27,9 +28,14 @@ class RocketBatch:
         self.seed = int(spec.seed if seed is None else seed)
         self.env_offset = int(env_offset)
         self.math_mode = {"exact": N.MATH_EXACT, "fast": N.MATH_FAST}[math_mode]
+        # precision of the integrated state: "f64" (reference parity <= 1e-9) or "f32" (6DOF, fast math; <= 1e-4, see rocket_f32.cuh)
+        self.precision = {"f64": N.F64, "f32": N.F32}[precision]
+        if self.precision == N.F32 and (spec.dof != 6 or self.math_mode != N.MATH_FAST):
+            raise ValueError("precision='f32' is implemented for the 6DOF environment with math_mode='fast'")
+        ydt = torch.float64 if self.precision == N.F64 else torch.float32
         n, nd, no, dev = self.n, spec.ndim, spec.nobs, self.device
         # persistent state (SoA)
-        self.y = torch.zeros((nd, n), dtype=torch.float64, device=dev)
+        self.y = torch.zeros((nd, n), dtype=ydt, device=dev)
         self.k = torch.zeros(n, dtype=torch.int32, device=dev)
         self.episode = torch.zeros(n, dtype=torch.int32, device=dev)
         self.v0 = torch.zeros(n, dtype=torch.float32, device=dev)
@@ -48,7 +54,7 @@ class RocketBatch:
         self.stats = torch.zeros(N.NSTATS, dtype=torch.int64, device=dev)
         self.debug = bool(debug_outputs)
         self.natt = torch.zeros(n, dtype=torch.int32, device=dev) if self.debug else None
-        self.y_pre_reset = torch.zeros((nd, n), dtype=torch.float64, device=dev) if self.debug else None
+        self.y_pre_reset = torch.zeros((nd, n), dtype=ydt, device=dev) if self.debug else None
         self.reward_terms = torch.zeros((6, n), dtype=torch.float64, device=dev) if self.debug else None
         self.vtarg = torch.zeros((4, n), dtype=torch.float64, device=dev) if self.debug else None
         self.launches = 0
@@ -105,7 +111,7 @@ class RocketBatch:
                 assert tuple(ic.shape) == (self.n, self.spec.ndim)
             if mask is not None:
                 mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
-            N.check(self.lib.rlr_reset(self._params_ref, N.F64, self._state(), _ptr(mask), _ptr(ic), _ptr(self.obs),
+            N.check(self.lib.rlr_reset(self._params_ref, self.precision, self._state(), _ptr(mask), _ptr(ic), _ptr(self.obs),
                                        self.n, self.env_offset, self.seed, self._stream()))
             self.launches += 1
         return self.obs
@@ -118,7 +124,7 @@ class RocketBatch:
             # hot path: no per-call allocation, one ctypes call
             if torch.cuda.current_device() != self._dev_index:
                 torch.cuda.set_device(self._dev_index)
-            rc = self._step_fn(self._params_ref, N.F64, self.math_mode, self._st, actions.data_ptr(),
+            rc = self._step_fn(self._params_ref, self.precision, self.math_mode, self._st, actions.data_ptr(),
                                N.ACT_PHYSICAL if physical else N.ACT_NORMALIZED, None, self._ot, self.n, self.env_offset, self.seed,
                                torch.cuda.current_stream(self._dev_index).cuda_stream)
             if rc:
@@ -131,7 +137,7 @@ class RocketBatch:
         with torch.cuda.device(self.device):
             if ic_inject is not None:
                 ic_inject = torch.as_tensor(ic_inject, dtype=torch.float32, device=self.device).contiguous()
-            N.check(self.lib.rlr_step(self._params_ref, N.F64, self.math_mode, self._state(), _ptr(actions), kind,
+            N.check(self.lib.rlr_step(self._params_ref, self.precision, self.math_mode, self._state(), _ptr(actions), kind,
                                       _ptr(ic_inject), self._out(), self.n, self.env_offset, self.seed, self._stream()))
             self.launches += 1
         return self.obs, self.reward, self.done
@@ -143,7 +149,7 @@ class RocketBatch:
         if kind is None:
             kind = N.ACT_PHYSICAL if physical else N.ACT_NORMALIZED
         with torch.cuda.device(self.device):
-            N.check(self.lib.rlr_rollout(self._params_ref, N.F64, self.math_mode, self._state(), _ptr(actions), kind, T,
+            N.check(self.lib.rlr_rollout(self._params_ref, self.precision, self.math_mode, self._state(), _ptr(actions), kind, T,
                                          _ptr(obs_buf), _ptr(reward_buf), _ptr(done_buf), _ptr(trunc_buf), _ptr(self.obs),
                                          _ptr(self.stats), self.n, self.env_offset, self.seed, self._stream()))
             self.launches += 1

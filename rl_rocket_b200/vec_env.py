@@ -39,12 +39,13 @@ class _LazyInfos(list):
 
 class RocketVecEnv(_VecEnvBase):
     def __init__(self, num_envs, dof=6, max_episode_steps=None, device="cuda:0", discrete_actions=False, discrete_table=None,
-                 reward_annealing=False, math_mode="fast", env_offset=0, trace_indices=None, trace_capacity=4096, **env_kwargs):
+                 reward_annealing=False, math_mode="fast", env_offset=0, trace_indices=None, trace_capacity=4096, precision="f64",
+                 **env_kwargs):
         table = (discrete_table or DEFAULT_DISCRETE_TABLE) if discrete_actions else None
         self.spec = EnvSpec(dof, max_episode_steps=max_episode_steps or 0, reward_mode=1 if reward_annealing else 0,
                             discrete_table=table, **env_kwargs)
         self.batch = RocketBatch(self.spec, num_envs, device=device, math_mode=math_mode, env_offset=env_offset,
-                                 debug_outputs=trace_indices is not None)
+                                 debug_outputs=trace_indices is not None, precision=precision)
         self.trace = TrajectoryTrace(self.batch, trace_indices, trace_capacity) if trace_indices is not None else None
         obs_space = spaces.Box(low=-1, high=1, shape=(self.spec.nobs,))
         act_space = spaces.Discrete(len(table)) if discrete_actions else spaces.Box(low=-1, high=1, shape=(self.spec.nact,))
@@ -201,7 +202,7 @@ class TrajectoryTrace:
             raise ValueError("trace_indices must be non-empty environment indices of this batch")
         m, nd, na, dev = self.idx.numel(), batch.spec.ndim, batch.spec.nact, batch.device
         self.capacity = int(capacity)
-        self.states = torch.zeros((self.capacity, m, nd), dtype=torch.float64, device=dev)
+        self.states = torch.zeros((self.capacity, m, nd), dtype=torch.float64, device=dev)       # (f32 states are widened on copy)
         self.actions = torch.zeros((self.capacity, m, na), dtype=torch.float32, device=dev)
         self.post = torch.zeros((self.capacity, m, nd), dtype=torch.float64, device=dev)      # state after auto-reset (next episode's IC)
         self.vtarg = torch.zeros((self.capacity, m, 4), dtype=torch.float64, device=dev)

@@ -47,7 +47,8 @@ def test_abi_argument_validation_without_gpu():
     bad = EnvSpec(6, **G.cfg6()).params
     bad.dof = 5
     assert lib.rlr_reset(ctypes.byref(bad), N.F64, st, None, None, None, 4, 0, 0, None) == -1
-    assert lib.rlr_reset(ctypes.byref(spec.params), N.F32, N.RlrState(1, 1, 1, 1, 1), None, None, None, 4, 0, 0, None) == -3
+    spec3d = EnvSpec(3, **G.cfg3())
+    assert lib.rlr_reset(ctypes.byref(spec3d.params), N.F32, N.RlrState(1, 1, 1, 1, 1), None, None, None, 4, 0, 0, None) == -3      # f32 state: 6DOF only
 
 
 def test_envspec_matches_reference_constants():
