@@ -405,7 +405,7 @@ RLR_DEV int rk45_solve(const typename S::Ctx& c, double t0, double t_bound, doub
     int status;
 #pragma unroll 1
     for (;;) {
-        if (h_abs < min_step) { status = -1; break; }
+        if (!(h_abs >= min_step)) { status = -1; break; }      // (negated form: a non-finite step size also ends the solve instead of looping forever)
         double t_new = t + h_abs;
         if (t_new - t_bound > 0) t_new = t_bound;
         const double h = t_new - t;
@@ -714,7 +714,7 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
     RLR_PHASE(1);                       // 1: make_ctx, K0, select_initial_step
 #pragma unroll 1
     for (;;) {
-        if (h_abs < min_step) { status = -1; break; }
+        if (!(h_abs >= min_step)) { status = -1; break; }      // (negated form: a non-finite step size also ends the solve instead of looping forever)
         double t_new = t + h_abs;
         if (t_new - t_bound > 0) t_new = t_bound;
         const double h = t_new - t;

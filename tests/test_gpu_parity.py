@@ -228,3 +228,48 @@ def test_empty_and_ragged_sizes():
     env0 = RocketBatch(spec, 0, seed=2)
     env0.reset()
     env0.step_tensor(torch.zeros((0, 3), device="cuda"))
+
+
+def test_config4_one_million_envs_sharded():
+    """BASELINE config 4 (2^20 envs = 8 x 131 072): the eight shards, stepped separately with their global env offsets, reproduce the
+    single full batch bit for bit (reset RNG and inputs keyed by the global index), and the shard statistics add up."""
+    EnvSpec, RocketBatch = _engine()
+    N, W, T = 1 << 20, 8, 3
+    spec = EnvSpec(6, max_episode_steps=800, **G.cfg6())
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = torch.rand((T, N, 3), device="cuda", generator=g) * 2 - 1
+    full = RocketBatch(spec, N, seed=21)
+    full.reset()
+    for t in range(T):
+        full.step_tensor(a[t])
+    tot = {k: 0 for k in ("steps", "attempts", "done")}
+    n = N // W
+    for r in range(W):
+        sh = RocketBatch(spec, n, seed=21, env_offset=r * n)
+        sh.reset()
+        for t in range(T):
+            sh.step_tensor(a[t, r * n:(r + 1) * n].contiguous())
+        assert torch.equal(sh.y, full.y[:, r * n:(r + 1) * n]) and torch.equal(sh.obs, full.obs[r * n:(r + 1) * n])
+        st = sh.read_stats()
+        for k in tot:
+            tot[k] += st[k]
+        del sh
+    fs = full.read_stats()
+    assert all(fs[k] == tot[k] for k in tot) and fs["steps"] == N * T
+
+
+def test_non_finite_state_ends_the_episode_instead_of_hanging():
+    """A NaN / Inf state (e.g. a user-injected initial condition) must not loop forever in the step-size controller: the solve reports
+    failure, which ends the episode exactly like scipy's status -1 does in the reference (rocket_env.py:702)."""
+    EnvSpec, RocketBatch = _engine()
+    spec = EnvSpec(6, max_episode_steps=800, **G.cfg6())
+    for mode in ("exact", "fast"):
+        env = RocketBatch(spec, 64, seed=1, math_mode=mode)
+        env.reset()
+        env.y[3, 5] = float("nan")
+        env.y[0, 9] = float("inf")
+        obs, rew, done = env.step_tensor(torch.zeros((64, 3), device="cuda"))
+        torch.cuda.synchronize()
+        d = done.cpu().numpy().astype(bool)
+        assert d[5] and d[9] and d.sum() == 2
+        assert torch.isfinite(env.y).all()          # both were reset
