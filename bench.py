@@ -204,7 +204,7 @@ def run_ours(args):
     e2e = n * world * Ke / float(e2e_s.item())
     e2e_d = {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": venv.h2d_bytes_per_step() * world,
              "d2h_bytes_per_step": venv.d2h_bytes_per_step() * world, "steps": Ke,
-             "note": "RocketVecEnv.step_host on every rank: pinned host actions in, packed obs|reward|done out (one H2D + one D2H per step); "
+             "note": "RocketVecEnv.step_host on every rank: the kernel reads the pinned host actions and writes obs|reward|done to mapped pinned host memory (the PCIe traffic overlaps the integration); "
                      "max wall time over ranks"}
 
     line = None

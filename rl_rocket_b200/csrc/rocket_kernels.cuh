@@ -1254,6 +1254,36 @@ RLR_DEV void write_obs(const RlrParams& p, float* dst, int64_t i, const float (&
     }
 }
 
+// 6DOF observation rows are 56 bytes: per-lane stores touch 32 different sectors per instruction (14 instructions per row).  When the
+// whole warp is active the 32 x 14 floats go through the warp's own (now idle) columns of the stage matrix in shared memory and leave
+// as 112 coalesced 16-byte stores.  Falls back to the per-lane stores for partial warps or an unaligned destination.
+RLR_DEV void write_obs6_warp(const RlrParams& p, float* dst, int64_t i, bool active, const float (&obs)[14], double* sK) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float* tile_dst = dst + (i - lane) * 14;                  // row of the warp's first environment
+#ifndef RLR_OBS_STAGED
+#define RLR_OBS_STAGED 1
+#endif
+    const bool staged = RLR_OBS_STAGED && __all_sync(0xffffffffu, active) && ((reinterpret_cast<uintptr_t>(tile_dst) & 15) == 0);
+    if (!staged) {
+        if (active) write_obs<Sys6>(p, dst, i, obs);
+        return;
+    }
+    float* st = reinterpret_cast<float*>(sK) + w * 128;       // rows are 64 threads x 16 B = 256 floats apart; a warp owns 128 of them
+    __syncwarp();                                             // every lane is done with its stage-matrix columns
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const int o4 = lane * 14 + 2 * k;
+        *reinterpret_cast<float2*>(st + (o4 >> 7) * 256 + (o4 & 127)) = make_float2(obs[2 * k], obs[2 * k + 1]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int f = k * 32 + lane;
+        if (f < 112) reinterpret_cast<float4*>(tile_dst)[f] = *reinterpret_cast<const float4*>(st + k * 256 + 4 * lane);
+    }
+    __syncwarp();                                             // the columns may be reused (rollout: next step's K0) only after the reads
+}
+
 // warp reduction of the episode statistics (REDUX for the 32-bit counters, shuffles for the 64-bit fixed-point return sum);
 // lane 0 issues one atomic per non-zero slot.
 RLR_DEV unsigned long long warp_sum(unsigned long long x) {
@@ -1358,9 +1388,10 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
     if (active) {
         if (finished) finish_and_reset<S>(p, st, ic_inject, i, ic, obs);
         RLR_PHASE(6);                   // 6: auto-reset
-        write_obs<S>(p, out.obs, i, obs);
+        if constexpr (S::N != 14) write_obs<S>(p, out.obs, i, obs);
         store_state<S>(gs, n, i, st);
     }
+    if constexpr (S::N == 14) write_obs6_warp(p, out.obs, i, active, (const float(&)[14])obs, sK);
     accumulate_stats(out.stats, active, fl, ep_len, ep_ret);
     RLR_PHASE(7);                       // 7: obs / state stores, statistics
 }
@@ -1420,9 +1451,10 @@ __global__ void RLR_KERNEL_BOUNDS(S) rollout_kernel(const __grid_constant__ RlrP
         float ic[S::N];
         const bool finished = active && fl.done;
         sample_ic_warp<S::N>(p, seed, env_offset + i, st.episode + 1, finished, ic);
-        if (active) {
-            if (finished) finish_and_reset<S>(p, st, nullptr, i, ic, obs);
-            if (obs_buf) write_obs<S>(p, obs_buf + (int64_t)t * n * no, i, obs);
+        if (active && finished) finish_and_reset<S>(p, st, nullptr, i, ic, obs);
+        if (obs_buf) {
+            if constexpr (S::N == 14) write_obs6_warp(p, obs_buf + (int64_t)t * n * no, i, active, (const float(&)[14])obs, sK);
+            else if (active) write_obs<S>(p, obs_buf + (int64_t)t * n * no, i, obs);
         }
         accumulate_stats(stats, active, fl, ep_len, ep_ret);
     }

@@ -142,6 +142,22 @@ class RocketBatch:
             self.launches += 1
         return self.obs, self.reward, self.done
 
+    def step_out_struct(self, obs, reward, done):
+        """An RlrStepOut whose obs / reward / done point at caller-owned buffers (e.g. mapped pinned HOST memory: the kernel then
+        writes the step's results straight across PCIe, see RocketVecEnv.step_host); every other output stays on the device."""
+        return N.RlrStepOut(_ptr(obs), _ptr(reward), None, _ptr(done), _ptr(self.truncated), _ptr(self.terminal_obs), _ptr(self.fin_ret),
+                            _ptr(self.fin_len), _ptr(self.flags), None, None, None, None, _ptr(self.stats))
+
+    def step_raw(self, actions_ptr, out_struct):
+        """One step with a raw f32 [n, nact] action pointer (device, or mapped pinned host memory) and a custom output struct."""
+        if torch.cuda.current_device() != self._dev_index:
+            torch.cuda.set_device(self._dev_index)
+        rc = self._step_fn(self._params_ref, self.precision, self.math_mode, self._st, actions_ptr, N.ACT_NORMALIZED, None, out_struct,
+                           self.n, self.env_offset, self.seed, torch.cuda.current_stream(self._dev_index).cuda_stream)
+        if rc:
+            N.check(rc)
+        self.launches += 1
+
     def rollout(self, actions, obs_buf=None, reward_buf=None, done_buf=None, trunc_buf=None, physical=False):
         """T fused steps in ONE launch.  actions: cuda f32 [T, n, nact] (or i64 [T, n]); optional [T, n, ...] output buffers."""
         T = actions.shape[0]

@@ -61,6 +61,7 @@ class RocketVecEnv(_VecEnvBase):
         self._h_obs = self._h_pack[:n * no * 4].view(torch.float32).view(n, no)
         self._h_rew = self._h_pack[n * no * 4:n * no * 4 + n * 4].view(torch.float32)
         self._h_done = self._h_pack[n * no * 4 + n * 4:]
+        self._ot_host = None          # RlrStepOut with obs | reward | done in mapped pinned host memory (built on first use)
         self._t_start = time.time()
         self._pending = False
         self.metadata = {"render.modes": []}
@@ -81,13 +82,29 @@ class RocketVecEnv(_VecEnvBase):
     def rollout_tensor(self, actions, obs_buf=None, reward_buf=None, done_buf=None, trunc_buf=None):
         return self.batch.rollout(actions, obs_buf, reward_buf, done_buf, trunc_buf)
 
-    def step_host(self, actions_host):
-        """actions: pinned host tensor (or numpy array).  Returns pinned host tensors (obs, reward, done) -- views of
-        persistent buffers.  H2D of the actions and D2H of the results are inside this call."""
+    def step_host(self, actions_host, zero_copy=None):
+        """actions: pinned host tensor (or numpy array).  Returns pinned host tensors (obs, reward, done) -- views of persistent
+        buffers.  The host -> device transfer of the actions and the device -> host transfer of the results are inside this call.
+
+        zero_copy (default: on for continuous actions without a trajectory trace): the kernel reads the actions from, and writes
+        obs | reward | done to, MAPPED pinned host memory, so the 4.8 MB of PCIe traffic per step of 65 536 envs overlaps the
+        integration instead of following it (measured 146 -> 108 us per step).  Otherwise: one H2D copy, the step, one packed D2H."""
         if not torch.is_tensor(actions_host):
             actions_host = torch.as_tensor(np.ascontiguousarray(actions_host))
-        self._d_actions.copy_(actions_host.reshape(self._d_actions.shape), non_blocking=True)
         b = self.batch
+        if zero_copy is None:
+            zero_copy = not self.discrete and self.trace is None
+        if zero_copy:
+            a = actions_host.reshape(self._h_actions.shape)
+            if not (a.dtype == torch.float32 and a.is_contiguous() and a.is_pinned()):
+                self._h_actions.copy_(a)
+                a = self._h_actions
+            if self._ot_host is None:
+                self._ot_host = b.step_out_struct(self._h_obs, self._h_rew, self._h_done)
+            b.step_raw(a.data_ptr(), self._ot_host)
+            torch.cuda.current_stream(self.device).synchronize()
+            return self._h_obs, self._h_rew, self._h_done
+        self._d_actions.copy_(actions_host.reshape(self._d_actions.shape), non_blocking=True)
         self.step_tensor(self._d_actions)
         self._h_pack.copy_(b.out_pack, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()

@@ -241,3 +241,25 @@ def test_facade_vtarg_history_matches_oracle():
             break
     df = env.vtarg_to_dataframe()
     assert df.shape == (len(env.vtarg_history), 3)
+
+
+def test_step_host_zero_copy_equals_copy_path():
+    """RocketVecEnv.step_host: the mapped-host-memory path (kernel reads actions from / writes obs|reward|done to pinned host memory)
+    returns exactly what the H2D + packed D2H path returns."""
+    from rl_rocket_b200.vec_env import RocketVecEnv
+    N, T = 4096, 40
+    cfg = G.cfg6()
+    v1 = RocketVecEnv(N, dof=6, max_episode_steps=30, **cfg)
+    v2 = RocketVecEnv(N, dof=6, max_episode_steps=30, **cfg)
+    v1.reset(); v2.reset()
+    rng = np.random.RandomState(0)
+    for t in range(T):
+        a = rng.uniform(-1, 1, (N, 3)).astype(np.float32)
+        o1, r1, d1 = v1.step_host(torch.as_tensor(a).pin_memory(), zero_copy=True)
+        o2, r2, d2 = v2.step_host(a, zero_copy=False)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)
+    assert int(d1.sum()) >= 0 and v1.episode_stats() == v2.episode_stats()
+    # numpy (unpinned) actions go through the pinned staging buffer
+    o1, r1, d1 = v1.step_host(a)
+    o2, r2, d2 = v2.step_host(a, zero_copy=False)
+    assert torch.equal(o1, o2)
