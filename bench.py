@@ -144,6 +144,9 @@ def run_ours(args):
 
     for t in range(W):
         env.step_tensor(actions[t])
+    if world > 1:        # warm-up of the collective too (the first NCCL all-gather sets up its channels: milliseconds)
+        for _ in range(3):
+            dist.all_gather_into_tensor(stat_gather, env.stats.unsqueeze(0))
     env.read_stats(reset=True)
     launches0 = env.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K + 1)]
