@@ -36,9 +36,6 @@
 #ifndef RLR_PHILOX_UNROLL
 #define RLR_PHILOX_UNROLL 0
 #endif
-#ifndef RLR_STAGE_UNROLL
-#define RLR_STAGE_UNROLL 0           // 1: the six RK stages as one basic block -- measured slower (spills at 128 registers)
-#endif
 
 namespace RLR_NS {
 
@@ -720,58 +717,12 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
         const double h = t_new - t;
         h_abs = fabs(h);
         ++natt;
-        double sv[3], sq[4], sw[3], sm = y[13], aB[3], aE[3];
+        double sv[3], sq[4], sw[3], sm = y[13];
+#if RLR_EXACT
+        double aB[3], aE[3];           // position rows of K are the stage velocities: accumulated on the fly (fast build: see the error norm)
 #pragma unroll
         for (int i = 0; i < 3; ++i) { aB[i] = y[3 + i] * B0; aE[i] = y[3 + i] * E0; }
-#if RLR_STAGE_UNROLL
-        // ---- rk_step (rk.py:14-71), stages unrolled.  The sums of stage s+1 over the rows already in shared memory are issued
-        // BEFORE the right-hand side of stage s (independent work for its reciprocal chain); the row just computed (K_s) is
-        // added from registers.  Same summation order as the rolled loop: j = 0 .. s.
-        double acc[10], accm;
-        {
-            const double a = c_RKA[1][0];
-#pragma unroll
-            for (int p = 0; p < 5; ++p) { const double2 k2 = KS2(0, p); acc[2 * p] = k2.x * a; acc[2 * p + 1] = k2.y * a; }
-            accm = c.dm * a;
-        }
-#pragma unroll
-        for (int s = 1; s <= 6; ++s) {
-#pragma unroll
-            for (int i = 0; i < 3; ++i) sv[i] = y[3 + i] + acc[i] * h;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) sq[i] = y[6 + i] + acc[3 + i] * h;
-#pragma unroll
-            for (int i = 0; i < 3; ++i) sw[i] = y[10 + i] + acc[7 + i] * h;
-            sm = y[13] + accm * h;
-            if (s <= 5) {
-                const double bs = c_RKB[s], es = c_RKE[s];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) { aB[i] += sv[i] * bs; aE[i] += sv[i] * es; }
-                const int sn = s + 1;
-                double a = c_RKA[sn][0];
-#pragma unroll
-                for (int p = 0; p < 5; ++p) { const double2 k2 = KS2(0, p); acc[2 * p] = k2.x * a; acc[2 * p + 1] = k2.y * a; }
-                accm = c.dm * a;
-#pragma unroll
-                for (int j = 1; j < s; ++j) {
-                    a = c_RKA[sn][j];
-#pragma unroll
-                    for (int p = 0; p < 5; ++p) { const double2 k2 = KS2(j, p); acc[2 * p] += k2.x * a; acc[2 * p + 1] += k2.y * a; }
-                    accm += c.dm * a;
-                }
-            }
-            rhs6r(c, sq, sw, sm, kk);
-            if (s <= 5) {
-                const double a = c_RKA[s + 1][s];
-#pragma unroll
-                for (int p = 0; p < 5; ++p) {
-                    KS2(s, p) = make_double2(kk[2 * p], kk[2 * p + 1]);
-                    acc[2 * p] += kk[2 * p] * a; acc[2 * p + 1] += kk[2 * p + 1] * a;
-                }
-                accm += c.dm * a;
-            }
-        }
-#else
+#endif
         // ---- rk_step (rk.py:14-71); stage 6 is y_new (row 6 of c_RKA = B).
         // Fast build: d(omega_x)/dt is identically zero (J_y == J_z, see rhs6r), so component 7 of the stage matrix is skipped and
         // omega_x keeps its value; dm is constant, so the mass stage value is m + (c_s h) dm.
@@ -818,11 +769,13 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
 #else
             sm = y[13] + (c_RKC[s] * h) * c.dm;
 #endif
+#if RLR_EXACT
             if (s <= 5) {
                 const double bs = c_RKB[s], es = c_RKE[s];
 #pragma unroll
                 for (int i = 0; i < 3; ++i) { aB[i] += sv[i] * bs; aE[i] += sv[i] * es; }
             }
+#endif
             rhs6r(c, sq, sw, sm, kk);
             if (s <= 5) {
                 double2* ko = sKt + s * KROW;
@@ -830,7 +783,6 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
                 for (int p = 0; p < 5; ++p) ko[p * BS6] = make_double2(kk[2 * p], kk[2 * p + 1]);
             }
         }
-#endif
         // ---- error norm (rk.py:101-107): components in index order r, v, q, w, m
         double rn[3];
         double ssum = 0.0;
@@ -839,12 +791,22 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
 #else
 #define RLR_ERR_TERM(num, yo, yn) ((num) * rcp1_(fma(absmax_(yo, yn), rtol, atol)))
 #endif
+#if RLR_EXACT
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
             rn[i] = y[i] + h * aB[i];
             const double e = RLR_ERR_TERM((aE[i] + sv[i] * E6) * h, y[i], rn[i]);
             ssum += e * e;
         }
+#else
+        // Fast build: position rows by quadrature of the acceleration rows instead of per-stage accumulators (12 registers less in
+        // the stage loop):  sum_s b_s v_s = v + h sum_j beta_j K_j,  beta_j = sum_s b_s a_sj = b_j (1 - c_j)  (= 0 for j = 1, 5), and
+        // sum_s e_s v_s = h sum_j eps_j K_j  because the error weights sum to zero (eps_j = sum_s e_s a_sj + e_6 b_j).  Evaluated in
+        // the loop below, where the dv rows are loaded anyway.
+        constexpr double BT0 = 35.0 / 384, BT2 = 50.0 / 159, BT3 = 25.0 / 192, BT4 = -243.0 / 6784;
+        constexpr double EP0 = -611.0 / 230400, EP2 = 514.0 / 83475, EP3 = -391.0 / 38400, EP4 = 4617.0 / 1356800, EP5 = 11.0 / 3360;
+        const double hsq = h * h;
+#endif
 #pragma unroll
         for (int p = 0; p < 5; ++p) {
             const double2 k0 = KS2(0, p), k2 = KS2(2, p), k3 = KS2(3, p), k4 = KS2(4, p), k5 = KS2(5, p);
@@ -854,10 +816,19 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
                 if (!RLR_LIVE(cc)) continue;          // K rows of omega_x are exactly zero in the fast build
                 const double yo = y[3 + cc];
                 const double yn = (cc < 3) ? sv[cc] : ((cc < 7) ? sq[cc - 3] : sw[cc - 7]);
-                const double es = hh ? (((((k0.y * E0 + k2.y * E2) + k3.y * E3) + k4.y * E4) + k5.y * E5) + kk[cc] * E6)
-                                     : (((((k0.x * E0 + k2.x * E2) + k3.x * E3) + k4.x * E4) + k5.x * E5) + kk[cc] * E6);
+                const double c0 = hh ? k0.y : k0.x, c2 = hh ? k2.y : k2.x, c3 = hh ? k3.y : k3.x, c4 = hh ? k4.y : k4.x, c5 = hh ? k5.y : k5.x;
+                const double es = ((((c0 * E0 + c2 * E2) + c3 * E3) + c4 * E4) + c5 * E5) + kk[cc] * E6;
                 const double e = RLR_ERR_TERM(es * h, yo, yn);
                 ssum += e * e;
+#if !RLR_EXACT
+                if (cc < 3) {          // the position component integrated from this acceleration row
+                    const double sb = ((c0 * BT0 + c2 * BT2) + c3 * BT3) + c4 * BT4;
+                    const double se = (((c0 * EP0 + c2 * EP2) + c3 * EP3) + c4 * EP4) + c5 * EP5;
+                    rn[cc] = y[cc] + (h * y[3 + cc] + hsq * sb);
+                    const double er = RLR_ERR_TERM(se * hsq, y[cc], rn[cc]);
+                    ssum += er * er;
+                }
+#endif
             }
         }
 #if RLR_EXACT
