@@ -85,13 +85,37 @@ RLR_DEV void rhs6f(const Ctx6f& c, const float (&q)[4], float wx, float wy, floa
 
 constexpr int BSF = 128;                         // threads per block
 constexpr int NKF = 9;                           // stage-matrix components per thread and stage
-constexpr size_t SMEMF_BYTES = 6 * NKF * BSF * sizeof(float);      // 27 KB per block
-#define KF(j, cc) sKt[((j) * NKF + (cc)) * BSF]
+// Stage row of a thread = two float4 (components 0..7) and one float (component 8): rows are [vec][tid] so that consecutive
+// threads touch consecutive 16-byte (4-byte) words -- three shared-memory instructions per row instead of nine.
+constexpr int ROWF = 9 * BSF;                    // floats per stage (8 * BSF in the float4 planes, BSF in the scalar plane)
+constexpr size_t SMEMF_BYTES = 6 * ROWF * sizeof(float);           // 27 KB per block
+struct KRow { float4 a, b; float c; };
+RLR_DEV KRow kf_load(const float* base, int j) {          // base = block's stage matrix, includes nothing thread specific
+    const float* r = base + j * ROWF;
+    KRow k;
+    k.a = reinterpret_cast<const float4*>(r)[threadIdx.x];
+    k.b = reinterpret_cast<const float4*>(r + 4 * BSF)[threadIdx.x];
+    k.c = r[8 * BSF + threadIdx.x];
+    return k;
+}
+RLR_DEV void kf_store(float* base, int j, const float (&v)[9]) {
+    float* r = base + j * ROWF;
+    reinterpret_cast<float4*>(r)[threadIdx.x] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(r + 4 * BSF)[threadIdx.x] = make_float4(v[4], v[5], v[6], v[7]);
+    r[8 * BSF + threadIdx.x] = v[8];
+}
+RLR_DEV void kf_unpack(const KRow& k, float (&v)[9]) {
+    v[0] = k.a.x; v[1] = k.a.y; v[2] = k.a.z; v[3] = k.a.w; v[4] = k.b.x; v[5] = k.b.y; v[6] = k.b.z; v[7] = k.b.w; v[8] = k.c;
+}
 
 // Terminal ground event: dense output (rk.py:554-565), safeguarded Newton root of the height quartic, state at the event.
 // buf = [y(14) | K6(9) | v_new(3) | dm h]; y(t_e) is written to buf[0..13].
-__device__ __noinline__ void event_path6f(const float* __restrict__ sKt, float* __restrict__ buf) {
+__device__ __noinline__ void event_path6f(const float* __restrict__ sKb, float* __restrict__ buf) {
     const float dm = buf[26], h = buf[27];
+    float K[6][9];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) kf_unpack(kf_load(sKb, j), K[j]);
+#define KF(j, cc) K[j][cc]
     float vs[6][3];
 #pragma unroll
     for (int s = 2; s <= 5; ++s) {
@@ -138,16 +162,16 @@ __device__ __noinline__ void event_path6f(const float* __restrict__ sKt, float* 
     buf[13] = YF(buf[13], dm, dm, dm, dm, dm, dm);
 #undef YF
 #undef QF
+#undef KF
 }
 
 // solve_ivp over one agent step in local time [0, dt]; returns 0 reached dt, 1 ground event, -1 step size underflow
-RLR_DEV int rk45_solve6f(const Ctx6f& c, float dt, float (&y)[14], int& natt, float* __restrict__ sKt) {
+RLR_DEV int rk45_solve6f(const Ctx6f& c, float dt, float (&y)[14], int& natt, float* __restrict__ sKb) {
     float kk[9];
     {
         const float q[4] = {y[6], y[7], y[8], y[9]};
         rhs6f(c, q, y[10], y[11], y[12], y[13], kk);
-#pragma unroll
-        for (int cc = 0; cc < NKF; ++cc) KF(0, cc) = kk[cc];
+        kf_store(sKb, 0, kk);
     }
     natt = 0;
     // state component of stage-matrix slot cc: 3 + cc for cc < 7 (v, q), 4 + cc for cc = 7, 8 (w_y, w_z)
@@ -204,16 +228,17 @@ RLR_DEV int rk45_solve6f(const Ctx6f& c, float dt, float (&y)[14], int& natt, fl
         // ---- rk_step (rk.py:14-71), rolled; stage 6 is y_new (row 6 of the table = B)
 #pragma unroll 1
         for (int s = 1; s <= 6; ++s) {
-            float acc[NKF];
+            float acc[NKF], kr[NKF];
             float a = cf_A[s][0];
+            kf_unpack(kf_load(sKb, 0), kr);
 #pragma unroll
-            for (int cc = 0; cc < NKF; ++cc) acc[cc] = KF(0, cc) * a;
-            const float* kp = sKt + NKF * BSF;
+            for (int cc = 0; cc < NKF; ++cc) acc[cc] = kr[cc] * a;
 #pragma unroll 1
-            for (int j = 1; j < s; ++j, kp += NKF * BSF) {
+            for (int j = 1; j < s; ++j) {
                 a = cf_A[s][j];
+                kf_unpack(kf_load(sKb, j), kr);
 #pragma unroll
-                for (int cc = 0; cc < NKF; ++cc) acc[cc] = fmaf(kp[cc * BSF], a, acc[cc]);
+                for (int cc = 0; cc < NKF; ++cc) acc[cc] = fmaf(kr[cc], a, acc[cc]);
             }
 #pragma unroll
             for (int i = 0; i < 3; ++i) sv[i] = fmaf(acc[i], h, y[3 + i]);
@@ -227,10 +252,7 @@ RLR_DEV int rk45_solve6f(const Ctx6f& c, float dt, float (&y)[14], int& natt, fl
                 for (int i = 0; i < 3; ++i) { aB[i] = fmaf(sv[i], bs, aB[i]); aE[i] = fmaf(sv[i], es, aE[i]); }
             }
             rhs6f(c, sq, y[10], swy, swz, sm, kk);
-            if (s <= 5) {
-#pragma unroll
-                for (int cc = 0; cc < NKF; ++cc) KF(s, cc) = kk[cc];
-            }
+            if (s <= 5) kf_store(sKb, s, kk);
         }
         // ---- error norm (rk.py:101-107)
         float rn[3], ssum = 0.0f;
@@ -240,11 +262,14 @@ RLR_DEV int rk45_solve6f(const Ctx6f& c, float dt, float (&y)[14], int& natt, fl
             const float e = (fmaf(sv[i], (float)E6, aE[i]) * h) * rcpf_(fmaf(absmaxf_(y[i], rn[i]), RTOLF, ATOLF));
             ssum = fmaf(e, e, ssum);
         }
+        float k0[NKF], k2[NKF], k3[NKF], k4[NKF], k5[NKF];
+        kf_unpack(kf_load(sKb, 0), k0); kf_unpack(kf_load(sKb, 2), k2); kf_unpack(kf_load(sKb, 3), k3);
+        kf_unpack(kf_load(sKb, 4), k4); kf_unpack(kf_load(sKb, 5), k5);
 #pragma unroll
         for (int cc = 0; cc < NKF; ++cc) {
             const float yo = y[YIDX(cc)];
             const float yn = (cc < 3) ? sv[cc] : ((cc < 7) ? sq[cc - 3] : (cc == 7 ? swy : swz));
-            const float es = ((((KF(0, cc) * (float)E0 + KF(2, cc) * (float)E2) + KF(3, cc) * (float)E3) + KF(4, cc) * (float)E4) + KF(5, cc) * (float)E5) +
+            const float es = ((((k0[cc] * (float)E0 + k2[cc] * (float)E2) + k3[cc] * (float)E3) + k4[cc] * (float)E4) + k5[cc] * (float)E5) +
                              kk[cc] * (float)E6;
             const float e = (es * h) * rcpf_(fmaf(absmaxf_(yo, yn), RTOLF, ATOLF));
             ssum = fmaf(e, e, ssum);
@@ -264,7 +289,7 @@ RLR_DEV int rk45_solve6f(const Ctx6f& c, float dt, float (&y)[14], int& natt, fl
 #pragma unroll
                 for (int i = 0; i < 3; ++i) ebuf[23 + i] = sv[i];
                 ebuf[26] = c.dm; ebuf[27] = h;
-                event_path6f(sKt, ebuf);
+                event_path6f(sKb, ebuf);
 #pragma unroll
                 for (int i = 0; i < 14; ++i) y[i] = ebuf[i];
                 status = 1;
@@ -275,8 +300,7 @@ RLR_DEV int rk45_solve6f(const Ctx6f& c, float dt, float (&y)[14], int& natt, fl
 #pragma unroll
             for (int i = 0; i < 4; ++i) y[6 + i] = sq[i];
             y[11] = swy; y[12] = swz; y[13] = sm;
-#pragma unroll
-            for (int cc = 0; cc < NKF; ++cc) KF(0, cc) = kk[cc];          // FSAL
+            kf_store(sKb, 0, kk);                                        // FSAL
             t = t_new;
             if (t - dt >= 0.0f) { status = 0; break; }
             rejected = false;
@@ -290,7 +314,6 @@ RLR_DEV int rk45_solve6f(const Ctx6f& c, float dt, float (&y)[14], int& natt, fl
 #undef YIDX
     return status;
 }
-#undef KF
 
 struct EnvStateF {
     float y[14];
@@ -337,7 +360,7 @@ RLR_DEV void env_step_f(const RlrParams& p, EnvStateF& st, const float (&u)[3], 
         c.dm = fdiv(-u[2], 3531.6f);
     }
     int natt;
-    const int status = rk45_solve6f(c, (float)p.dt, st.y, natt, sK + threadIdx.x);
+    const int status = rk45_solve6f(c, (float)p.dt, st.y, natt, sK);
     {
         const float n2 = ((st.y[6] * st.y[6] + st.y[7] * st.y[7]) + st.y[8] * st.y[8]) + st.y[9] * st.y[9];
         const float rnq = rsqrtf_(n2);
