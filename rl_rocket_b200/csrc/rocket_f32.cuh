@@ -378,8 +378,35 @@ RLR_DEV void env_step_f(const RlrParams& p, EnvStateF& st, const float (&u)[3], 
     fl.viol = res.viol; fl.landed = res.landed; fl.status = status; fl.natt = natt;
 }
 
+// coalesced observation rows through the warp's own (idle) float4 planes of stage rows 0 and 1 -- see write_obs6_warp
+RLR_DEV void write_obs6_warp_f(const RlrParams& p, float* dst, int64_t i, bool active, const float (&obs)[14], float* sKb, bool stage) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float* tile_dst = dst + (i - lane) * 14;
+    const bool staged = stage && __all_sync(0xffffffffu, active) && ((reinterpret_cast<uintptr_t>(tile_dst) & 15) == 0);
+    if (!staged) {
+        if (active) write_obs<Sys6>(p, dst, i, obs);
+        return;
+    }
+    // plane k (128 floats per warp): row 0 plane a, row 0 plane b, row 1 plane a, row 1 plane b
+    auto plane = [&](int k) { return sKb + (k >> 1) * ROWF + (k & 1) * 4 * BSF + w * 128; };
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 7; ++k) {
+        const int o4 = lane * 14 + 2 * k;
+        *reinterpret_cast<float2*>(plane(o4 >> 7) + (o4 & 127)) = make_float2(obs[2 * k], obs[2 * k + 1]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int f = k * 32 + lane;
+        if (f < 112) reinterpret_cast<float4*>(tile_dst)[f] = *reinterpret_cast<const float4*>(plane(k) + 4 * lane);
+    }
+    __syncwarp();
+}
+
 __global__ void __launch_bounds__(BSF) step_kernel_f32(const __grid_constant__ RlrParams p, RlrState gs, const float* actions, int action_kind,
-                                                       const float* ic_inject, RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed) {
+                                                       const float* ic_inject, RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed,
+                                                       bool stage_obs) {
     extern __shared__ float sKf[];
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n;
@@ -433,9 +460,9 @@ __global__ void __launch_bounds__(BSF) step_kernel_f32(const __grid_constant__ R
             }
             reset_from_ic_f(p, ic, st, obs);
         }
-        write_obs<Sys6>(p, out.obs, i, obs);
         store_state_f(gs, n, i, st);
     }
+    write_obs6_warp_f(p, out.obs, i, active, obs, sKf, stage_obs);
     accumulate_stats(out.stats, active, fl, ep_len, ep_ret);
 }
 

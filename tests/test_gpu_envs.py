@@ -243,14 +243,15 @@ def test_facade_vtarg_history_matches_oracle():
     assert df.shape == (len(env.vtarg_history), 3)
 
 
-def test_step_host_zero_copy_equals_copy_path():
+@pytest.mark.parametrize("precision", ["f64", "f32"])
+def test_step_host_zero_copy_equals_copy_path(precision):
     """RocketVecEnv.step_host: the mapped-host-memory path (kernel reads actions from / writes obs|reward|done to pinned host memory)
     returns exactly what the H2D + packed D2H path returns."""
     from rl_rocket_b200.vec_env import RocketVecEnv
     N, T = 4096, 40
     cfg = G.cfg6()
-    v1 = RocketVecEnv(N, dof=6, max_episode_steps=30, **cfg)
-    v2 = RocketVecEnv(N, dof=6, max_episode_steps=30, **cfg)
+    v1 = RocketVecEnv(N, dof=6, max_episode_steps=30, precision=precision, **cfg)
+    v2 = RocketVecEnv(N, dof=6, max_episode_steps=30, precision=precision, **cfg)
     v1.reset(); v2.reset()
     rng = np.random.RandomState(0)
     for t in range(T):
