@@ -264,3 +264,37 @@ def test_step_host_zero_copy_equals_copy_path(precision):
     o1, r1, d1 = v1.step_host(a)
     o2, r2, d2 = v2.step_host(a, zero_copy=False)
     assert torch.equal(o1, o2)
+
+
+def test_step_is_cuda_graph_capturable():
+    """rlr_step only enqueues work on the caller's stream (no allocation, no synchronisation), so a sequence of steps can be captured
+    into a CUDA graph and replayed; the replay reproduces the eager trajectory bit for bit."""
+    from rl_rocket_b200.config import EnvSpec
+    from rl_rocket_b200.engine import RocketBatch
+    N, T = 4096, 8
+    spec = EnvSpec(6, max_episode_steps=800, **G.cfg6())
+    a = torch.rand((T, N, 3), device="cuda") * 2 - 1
+    eager = RocketBatch(spec, N, seed=9); eager.reset()
+    graphed = RocketBatch(spec, N, seed=9); graphed.reset()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):                       # warm-up on the capture stream (launch geometry / attribute queries happen here)
+        graphed.step_tensor(a[0])
+    side.synchronize()
+    graphed.reset()
+    obs_hist = torch.zeros((T, N, 14), device="cuda")
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=side):
+        for t in range(T):
+            o, r, d = graphed.step_tensor(a[t])
+            obs_hist[t].copy_(o)
+    g.replay()
+    torch.cuda.synchronize()
+    for t in range(T):
+        o, r, d = eager.step_tensor(a[t])
+        assert torch.equal(o, obs_hist[t])
+    assert torch.equal(eager.y, graphed.y) and torch.equal(eager.k, graphed.k)
+    g.replay()                                           # a second replay continues the trajectories
+    torch.cuda.synchronize()
+    for t in range(T):
+        eager.step_tensor(a[t])
+    assert torch.equal(eager.y, graphed.y)
