@@ -59,6 +59,25 @@ RLR_DEV float powf_p02(float x) { const float y = powf_m02(x), y2 = y * y; retur
 RLR_DEV float absmaxf_(float a, float b) { return fmaxf(fabsf(a), fabsf(b)); }
 RLR_DEV float min_stepf_at(float t) { return 10.0f * fabsf(__int_as_float(__float_as_int(t) + 1) - t); }      // t >= 0
 
+// Packed binary32 arithmetic (Blackwell FFMA2 / FMUL2: two lanes of a 64-bit register pair per instruction).  The f32 kernels are
+// instruction-issue bound (69 % of the issue slots, profiles/r01d_f32_kernels_ncu.txt); the stage sums, stage states and error
+// estimates are pairwise-independent, so packing them halves their instruction count.
+RLR_DEV float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;"
+        : "=l"(reinterpret_cast<unsigned long long&>(d))
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)), "l"(reinterpret_cast<unsigned long long&>(c)));
+    return d;
+}
+RLR_DEV float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;"
+        : "=l"(reinterpret_cast<unsigned long long&>(d))
+        : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+    return d;
+}
+RLR_DEV float2 bc2(float x) { return make_float2(x, x); }
+
 struct Ctx6f { float Tb0, Tb1, Tb2, tau1, tau2, dm; };
 
 // d = [dv(3), dq(4), dw_y, dw_z]   (dw_x == 0: J_y == J_z)
@@ -222,58 +241,82 @@ RLR_DEV int rk45_solve6f(const Ctx6f& c, float dt, float (&y)[14], int& natt, fl
         const float h = t_new - t;
         h_abs = fabsf(h);
         ++natt;
-        float sv[3], sq[4], swy = y[11], swz = y[12], sm = y[13], aB[3], aE[3];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) { aB[i] = y[3 + i] * (float)B0; aE[i] = y[3 + i] * (float)E0; }
+        // Components with a stage-matrix row, packed in pairs: (v0,v1) (v2,q0) (q1,q2) (q3,wy) and the scalar wz
+        const float2 yp0 = make_float2(y[3], y[4]), yp1 = make_float2(y[5], y[6]), yp2 = make_float2(y[7], y[8]), yp3 = make_float2(y[9], y[11]);
+        float2 sp0 = yp0, sp1 = yp1, sp2 = yp2, sp3 = yp3;
+        float swz = y[12], sm = y[13];
+        const float2 h2 = bc2(h);
         // ---- rk_step (rk.py:14-71), rolled; stage 6 is y_new (row 6 of the table = B)
 #pragma unroll 1
         for (int s = 1; s <= 6; ++s) {
-            float acc[NKF], kr[NKF];
-            float a = cf_A[s][0];
-            kf_unpack(kf_load(sKb, 0), kr);
-#pragma unroll
-            for (int cc = 0; cc < NKF; ++cc) acc[cc] = kr[cc] * a;
+            float2 a2 = bc2(cf_A[s][0]);
+            KRow k = kf_load(sKb, 0);
+            float2 acc0 = fmul2(make_float2(k.a.x, k.a.y), a2), acc1 = fmul2(make_float2(k.a.z, k.a.w), a2);
+            float2 acc2 = fmul2(make_float2(k.b.x, k.b.y), a2), acc3 = fmul2(make_float2(k.b.z, k.b.w), a2);
+            float accs = k.c * a2.x;
 #pragma unroll 1
             for (int j = 1; j < s; ++j) {
-                a = cf_A[s][j];
-                kf_unpack(kf_load(sKb, j), kr);
-#pragma unroll
-                for (int cc = 0; cc < NKF; ++cc) acc[cc] = fmaf(kr[cc], a, acc[cc]);
+                a2 = bc2(cf_A[s][j]);
+                k = kf_load(sKb, j);
+                acc0 = ffma2(make_float2(k.a.x, k.a.y), a2, acc0); acc1 = ffma2(make_float2(k.a.z, k.a.w), a2, acc1);
+                acc2 = ffma2(make_float2(k.b.x, k.b.y), a2, acc2); acc3 = ffma2(make_float2(k.b.z, k.b.w), a2, acc3);
+                accs = fmaf(k.c, a2.x, accs);
             }
-#pragma unroll
-            for (int i = 0; i < 3; ++i) sv[i] = fmaf(acc[i], h, y[3 + i]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) sq[i] = fmaf(acc[3 + i], h, y[6 + i]);
-            swy = fmaf(acc[7], h, y[11]); swz = fmaf(acc[8], h, y[12]);
+            sp0 = ffma2(acc0, h2, yp0); sp1 = ffma2(acc1, h2, yp1); sp2 = ffma2(acc2, h2, yp2); sp3 = ffma2(acc3, h2, yp3);
+            swz = fmaf(accs, h, y[12]);
             sm = fmaf(cf_C[s] * h, c.dm, y[13]);
-            if (s <= 5) {
-                const float bs = cf_B[s], es = cf_E[s];
-#pragma unroll
-                for (int i = 0; i < 3; ++i) { aB[i] = fmaf(sv[i], bs, aB[i]); aE[i] = fmaf(sv[i], es, aE[i]); }
-            }
-            rhs6f(c, sq, y[10], swy, swz, sm, kk);
+            const float sq[4] = {sp1.y, sp2.x, sp2.y, sp3.x};
+            rhs6f(c, sq, y[10], sp3.y, swz, sm, kk);
             if (s <= 5) kf_store(sKb, s, kk);
         }
-        // ---- error norm (rk.py:101-107)
+        // ---- error norm (rk.py:101-107).  Position rows by quadrature of the acceleration rows (see rk45_solve6):
+        //      sum_s b_s v_s = v + h sum_j beta_j K_j,  sum_s e_s v_s = h sum_j eps_j K_j
         float rn[3], ssum = 0.0f;
+        {
+            constexpr float BT0 = (float)(35.0 / 384), BT2 = (float)(50.0 / 159), BT3 = (float)(25.0 / 192), BT4 = (float)(-243.0 / 6784);
+            constexpr float EP0 = (float)(-611.0 / 230400), EP2 = (float)(514.0 / 83475), EP3 = (float)(-391.0 / 38400),
+                            EP4 = (float)(4617.0 / 1356800), EP5 = (float)(11.0 / 3360);
+            const KRow k0 = kf_load(sKb, 0), k2 = kf_load(sKb, 2), k3 = kf_load(sKb, 3), k4 = kf_load(sKb, 4), k5 = kf_load(sKb, 5);
+#define PAIR(k, i) ((i) == 0 ? make_float2(k.a.x, k.a.y) : (i) == 1 ? make_float2(k.a.z, k.a.w) : (i) == 2 ? make_float2(k.b.x, k.b.y) : make_float2(k.b.z, k.b.w))
+            float2 es[4];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) {
-            rn[i] = fmaf(h, aB[i], y[i]);
-            const float e = (fmaf(sv[i], (float)E6, aE[i]) * h) * rcpf_(fmaf(absmaxf_(y[i], rn[i]), RTOLF, ATOLF));
-            ssum = fmaf(e, e, ssum);
-        }
-        float k0[NKF], k2[NKF], k3[NKF], k4[NKF], k5[NKF];
-        kf_unpack(kf_load(sKb, 0), k0); kf_unpack(kf_load(sKb, 2), k2); kf_unpack(kf_load(sKb, 3), k3);
-        kf_unpack(kf_load(sKb, 4), k4); kf_unpack(kf_load(sKb, 5), k5);
+            for (int i = 0; i < 4; ++i) {
+                float2 e = fmul2(PAIR(k0, i), bc2((float)E0));
+                e = ffma2(PAIR(k2, i), bc2((float)E2), e);
+                e = ffma2(PAIR(k3, i), bc2((float)E3), e);
+                e = ffma2(PAIR(k4, i), bc2((float)E4), e);
+                e = ffma2(PAIR(k5, i), bc2((float)E5), e);
+                es[i] = ffma2(make_float2(kk[2 * i], kk[2 * i + 1]), bc2((float)E6), e);
+            }
+            const float ess = ((((k0.c * (float)E0 + k2.c * (float)E2) + k3.c * (float)E3) + k4.c * (float)E4) + k5.c * (float)E5) + kk[8] * (float)E6;
+            // position: pair (r0, r1) from the (dv0, dv1) rows, r2 from dv2
+            float2 sb = fmul2(PAIR(k0, 0), bc2(BT0)), se = fmul2(PAIR(k0, 0), bc2(EP0));
+            sb = ffma2(PAIR(k2, 0), bc2(BT2), sb); se = ffma2(PAIR(k2, 0), bc2(EP2), se);
+            sb = ffma2(PAIR(k3, 0), bc2(BT3), sb); se = ffma2(PAIR(k3, 0), bc2(EP3), se);
+            sb = ffma2(PAIR(k4, 0), bc2(BT4), sb); se = ffma2(PAIR(k4, 0), bc2(EP4), se);
+            se = ffma2(PAIR(k5, 0), bc2(EP5), se);
+            const float sb2 = ((k0.a.z * BT0 + k2.a.z * BT2) + k3.a.z * BT3) + k4.a.z * BT4;
+            const float se2 = (((k0.a.z * EP0 + k2.a.z * EP2) + k3.a.z * EP3) + k4.a.z * EP4) + k5.a.z * EP5;
+#undef PAIR
+            const float hsq = h * h;
+            const float sbv[3] = {sb.x, sb.y, sb2}, sev[3] = {se.x, se.y, se2};
 #pragma unroll
-        for (int cc = 0; cc < NKF; ++cc) {
-            const float yo = y[YIDX(cc)];
-            const float yn = (cc < 3) ? sv[cc] : ((cc < 7) ? sq[cc - 3] : (cc == 7 ? swy : swz));
-            const float es = ((((k0[cc] * (float)E0 + k2[cc] * (float)E2) + k3[cc] * (float)E3) + k4[cc] * (float)E4) + k5[cc] * (float)E5) +
-                             kk[cc] * (float)E6;
-            const float e = (es * h) * rcpf_(fmaf(absmaxf_(yo, yn), RTOLF, ATOLF));
-            ssum = fmaf(e, e, ssum);
+            for (int i = 0; i < 3; ++i) {
+                rn[i] = y[i] + fmaf(hsq, sbv[i], h * y[3 + i]);
+                const float e = (sev[i] * hsq) * rcpf_(fmaf(absmaxf_(y[i], rn[i]), RTOLF, ATOLF));
+                ssum = fmaf(e, e, ssum);
+            }
+            const float esv[9] = {es[0].x, es[0].y, es[1].x, es[1].y, es[2].x, es[2].y, es[3].x, es[3].y, ess};
+            const float ynv[9] = {sp0.x, sp0.y, sp1.x, sp1.y, sp2.x, sp2.y, sp3.x, sp3.y, swz};
+#pragma unroll
+            for (int cc = 0; cc < NKF; ++cc) {
+                const float e = (esv[cc] * h) * rcpf_(fmaf(absmaxf_(y[YIDX(cc)], ynv[cc]), RTOLF, ATOLF));
+                ssum = fmaf(e, e, ssum);
+            }
         }
+        const float sv[3] = {sp0.x, sp0.y, sp1.x};
+        const float sq[4] = {sp1.y, sp2.x, sp2.y, sp3.x};
+        const float swy = sp3.y;
         const float err = sqrtf_(ssum) * INV_RS14F;
         if (err < 1.0f) {
             float factor = (err == 0.0f) ? 10.0f : fminf(10.0f, 0.9f * powf_m02(err));
