@@ -744,6 +744,7 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
 #if RLR_EXACT
             double accm = c.dm * a;
 #endif
+#if RLR_EXACT
             const double2* kp = sKt + KROW;
 #pragma unroll 1
             for (int j = 1; j < s; ++j, kp += KROW) {
@@ -752,12 +753,26 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
                 for (int p = 0; p < 5; ++p) {
                     const double2 k2 = kp[p * BS6];
                     acc[2 * p] += k2.x * a;
-                    if (RLR_LIVE(2 * p + 1)) acc[2 * p + 1] += k2.y * a;
+                    acc[2 * p + 1] += k2.y * a;
                 }
-#if RLR_EXACT
                 accm += c.dm * a;
-#endif
             }
+#else
+            // rows 1 .. s-1: unrolled with warp-uniform guards, so that every shared-memory and constant-bank address is base +
+            // immediate (the rolled form stalls on the write-after-read hazards of its index registers: 5 % of a lone warp's time)
+#pragma unroll
+            for (int j = 1; j <= 5; ++j) {
+                if (j < s) {
+                    const double aj = c_RKA[s][j];
+#pragma unroll
+                    for (int p = 0; p < 5; ++p) {
+                        const double2 k2 = KS2(j, p);
+                        acc[2 * p] += k2.x * aj;
+                        if (RLR_LIVE(2 * p + 1)) acc[2 * p + 1] += k2.y * aj;
+                    }
+                }
+            }
+#endif
 #pragma unroll
             for (int i = 0; i < 3; ++i) sv[i] = y[3 + i] + acc[i] * h;
 #pragma unroll
