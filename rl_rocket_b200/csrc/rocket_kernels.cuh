@@ -30,12 +30,6 @@
 #ifndef RLR_NS
 #error "define RLR_NS before including rocket_kernels.cuh"
 #endif
-#ifndef RLR_EVENT_NEWTON
-#define RLR_EVENT_NEWTON (!RLR_EXACT)   // fast build: Newton root of the height quartic, Brent as the fallback (see event_path6)
-#endif
-#ifndef RLR_PHILOX_UNROLL
-#define RLR_PHILOX_UNROLL 0
-#endif
 
 namespace RLR_NS {
 
@@ -129,17 +123,13 @@ RLR_DEV double rcp_(double x) {
     r = fma(r, e, r);
     return r;
 }
-// reciprocal of an error-control scale (atol + rtol |y|): hardware seed + RLR_RCP1_NEWTON Newton steps.  These factors only
+// reciprocal of an error-control scale (atol + rtol |y|): hardware seed + ONE Newton step (1e-12).  These factors only
 // weight the RMS norms that choose the step size, where a relative error of 1e-12 moves h by 1e-13 and the state by < 1e-15.
-#ifndef RLR_RCP1_NEWTON
-#define RLR_RCP1_NEWTON 1
-#endif
 RLR_DEV double rcp1_(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-#pragma unroll
-    for (int it = 0; it < RLR_RCP1_NEWTON; ++it) { const double e = fma(-x, r, 1.0); r = fma(r, e, r); }
-    return r;
+    const double e = fma(-x, r, 1.0);
+    return fma(r, e, r);
 }
 // max(|a|, |b|) with one compare and two selects (fmax() expands to a NaN-aware six-instruction sequence)
 RLR_DEV double absmax_(double a, double b) { const double fa = fabs(a), fb = fabs(b); return (fa > fb) ? fa : fb; }
@@ -594,7 +584,7 @@ __device__ __noinline__ void event_path6(const double2* __restrict__ sKt, double
     const double hq0 = vx0, hq1 = DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 1),
                  hq2 = DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 2),
                  hq3 = DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 3);
-#if RLR_EVENT_NEWTON
+#if !RLR_EXACT
     // Fast build: the root of the height quartic  g(x) = r0 + h x (q0 + x (q1 + x (q2 + x q3))),  x = (t_e - t) / h in [0, 1],  by
     // Newton's method from the secant point (quadratic convergence: 5 steps reach the rounding floor; Brent's bisection /
     // inverse-quadratic steps with their IEEE divisions were the longest serial chain of the launch).  Anything unexpected
@@ -951,11 +941,7 @@ RLR_DEV void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
 
 template <int N>
 RLR_DEV void sample_ic(const RlrParams& p, uint64_t seed, int64_t env, int32_t episode, float (&ic)[N]) {
-#if RLR_PHILOX_UNROLL
-#pragma unroll
-#else
 #pragma unroll 1
-#endif
     for (int b = 0; b * 2 < N; ++b) {      // rolled: the reset path is rare per thread, keep its code small
         uint32_t c[4] = {(uint32_t)b, (uint32_t)episode, (uint32_t)((uint64_t)env & 0xffffffffu), (uint32_t)((uint64_t)env >> 32)};
         philox4x32_10(c, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
