@@ -210,6 +210,32 @@ def run_ours(args):
              "note": "RocketVecEnv.step_host on every rank: the kernel reads the pinned host actions and writes obs|reward|done to mapped pinned host memory (the PCIe traffic overlaps the integration); "
                      "max wall time over ranks"}
 
+    # ---- BASELINE config 4 for the record: 2^20 environments in total, sharded over the ranks by global index (2^20 / world per GPU),
+    # one launch per step, back to back, device-timed, max over ranks, the statistics all-gather included
+    del venv
+    n4 = (1 << 20) // world
+    K4 = min(K, 100)
+    env4 = RocketBatch(spec, n4, device=dev, seed=42, env_offset=rank * n4, math_mode=args.math)
+    env4.reset()
+    a4 = torch.empty((8, n4, 3), device=dev)
+    a4.uniform_(-1, 1, generator=gen)
+    for t in range(PREP_STEPS):
+        env4.step_tensor(a4[t % 8])
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for t in range(K4):
+        env4.step_tensor(a4[t % 8])
+    if world > 1:
+        dist.all_gather_into_tensor(stat_gather, env4.stats.unsqueeze(0))
+    c1.record()
+    c1.synchronize()
+    t4 = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t4, op=dist.ReduceOp.MAX)
+    config4 = n4 * world * K4 / (float(t4.item()) * 1e-3)
+    del env4, a4
+
     line = None
     if rank == 0:
         # ---- back-to-back (no flush) and fused-rollout variants, device-timed, for the record
@@ -285,7 +311,8 @@ def run_ours(args):
                 "clocks": clocks, "e2e": e2e_d, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "episodes_finished": st_all["done"], "wall_ms_timed_region": wall_ms,
                 "variants": {"back_to_back_no_flush": b2b, "fused_rollout_kernel": fused, "f32_state_back_to_back": f32_b2b,
-                             "f32_state_fused_rollout": f32_fused, "unit": "env-steps/s (rank 0 only)"}}
+                             "f32_state_fused_rollout": f32_fused, "unit": "env-steps/s (rank 0 only)",
+                             "config4_2p20_envs_sharded_all_ranks": config4}}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
