@@ -40,4 +40,20 @@ def zc2(act_host):
     N.check(b.lib.rlr_step(b._params_ref, N.F64, b.math_mode, b._st, act_host.data_ptr(), 0, None, ot, n, 0, b.seed, stream))
     torch.cuda.current_stream().synchronize()
 print(f"zero-copy in + out:     {run(zc2):.1f} us/step")
+ot2 = N.RlrStepOut(_ptr(h_obs), _ptr(b.reward), None, _ptr(b.done), _ptr(b.truncated), _ptr(b.terminal_obs), _ptr(b.fin_ret), _ptr(b.fin_len),
+                   _ptr(b.flags), None, None, None, None, _ptr(b.stats))
+def zc3(act_host):
+    N.check(b.lib.rlr_step(b._params_ref, N.F64, b.math_mode, b._st, act_host.data_ptr(), 0, None, ot2, n, 0, b.seed, stream))
+    torch.cuda.current_stream().synchronize()
+print(f"zero-copy in + obs only (reward/done stay on device): {run(zc3):.1f} us/step")
+ot3 = N.RlrStepOut(_ptr(b.obs), _ptr(b.reward), None, _ptr(b.done), _ptr(b.truncated), _ptr(b.terminal_obs), _ptr(b.fin_ret), _ptr(b.fin_len),
+                   _ptr(b.flags), None, None, None, None, _ptr(b.stats))
+def zc4(act_host):
+    N.check(b.lib.rlr_step(b._params_ref, N.F64, b.math_mode, b._st, act_host.data_ptr(), 0, None, ot3, n, 0, b.seed, stream))
+    torch.cuda.current_stream().synchronize()
+print(f"zero-copy in only (all outputs on device): {run(zc4):.1f} us/step")
+def dev_only(act_host):
+    N.check(b.lib.rlr_step(b._params_ref, N.F64, b.math_mode, b._st, d_act.data_ptr(), 0, None, ot3, n, 0, b.seed, stream))
+    torch.cuda.current_stream().synchronize()
+print(f"device only + sync: {run(dev_only):.1f} us/step")
 print("obs finite:", bool(torch.isfinite(h_obs).all()), "done sum", int(h_done.sum()))
