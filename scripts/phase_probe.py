@@ -1,6 +1,6 @@
 """Development aid: per-phase warp cycles of step_kernel<Sys6> from a -DRLR_PHASE_TIMING=1 tuning build.
 usage: RLR_LIB=rl_rocket_b200/_C/librlrocket_PT.so python scripts/phase_probe.py"""
-import ctypes as C, os, sys, json
+import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from rl_rocket_b200 import _native as N

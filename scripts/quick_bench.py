@@ -1,9 +1,9 @@
 """Ad-hoc timing probe (development aid; bench.py is the contract benchmark)."""
-import sys, os, json, time
+import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from rl_rocket_b200.config import EnvSpec
-from rl_rocket_b200.engine import RocketBatch, fma_peak
+from rl_rocket_b200.engine import RocketBatch
 from tests import goldutil as G
 
 def timeit(fn, n):

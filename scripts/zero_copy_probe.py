@@ -1,11 +1,11 @@
 """Development probe: end-to-end step with the kernel writing obs|reward|done straight into mapped pinned host memory (zero-copy)
 versus the packed D2H copy of RocketVecEnv.step_host."""
-import os, sys, time, ctypes as C
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from rl_rocket_b200 import _native as N
-from rl_rocket_b200.config import EnvSpec
-from rl_rocket_b200.engine import RocketBatch, _ptr
+
+from rl_rocket_b200.engine import _ptr
 from rl_rocket_b200.vec_env import RocketVecEnv
 from tests import goldutil as G
 
