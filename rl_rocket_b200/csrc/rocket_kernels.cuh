@@ -180,6 +180,35 @@ RLR_DEV double pow_p02(double x) {          // x^(1/5) = x * (x^(-1/5))^4
 #define RLR_DIV(a, b) ((a) * rcp_(b))
 #endif
 
+#if !RLR_EXACT
+// sin and cos of a moderate argument (|x| < ~1e5; the 3DOF pitch angle is wrapped to [0, 2 pi) every step) in ~35 FP64 instructions:
+// three-term Cody-Waite reduction by pi/2 and the fdlibm kernel polynomials on [-pi/4, pi/4] (< 1 ulp each).  libdevice's sincos()
+// carries the Payne-Hanek path for huge arguments and costs more than twice as much; the 3DOF right-hand side is dominated by it.
+RLR_DEV void sincos_fast(double x, double* sn, double* cs) {
+    const double n = rint(x * 6.36619772367581382433e-01);          // x * 2 / pi
+    double r = fma(-n, 1.57079632673412561417e+00, x);               // pi/2 in three parts (fdlibm pio2_1, pio2_2, pio2_3)
+    r = fma(-n, 6.07710050630396597660e-11, r);
+    r = fma(-n, 2.02226624879595063154e-21, r);
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double s0 = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double c0 = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const int q = (int)n & 3;
+    const double sa = (q & 1) ? c0 : s0, ca = (q & 1) ? s0 : c0;
+    *sn = (q & 2) ? -sa : sa;
+    *cs = ((q + 1) & 2) ? -ca : ca;
+}
+#endif
+
 // ------------------------------------------------------------------ Dormand-Prince tableau
 #define A10 (1.0 / 5)
 #define A20 (3.0 / 40)
@@ -280,11 +309,14 @@ struct Sys6 {
 // 3DOF: y = [x, z, theta, vx, vz, omega, m]   (simulator.py:88-130)
 struct Sys3 {
     static constexpr int N = 7, EV = 1, NA = 2, NOBS = 7, MAX_REGS = 168;
-    struct Ctx { double delta, T, torque, dm; };
+    struct Ctx { double delta, T, torque, dm, sd, cd; };
 
     RLR_DEV static void make_ctx(Ctx& c, const float* u) {
         c.delta = (double)u[0];
         c.T = (double)u[1];
+#if !RLR_EXACT
+        sincos(c.delta, &c.sd, &c.cd);      // fast build: sin / cos (delta + phi) by angle addition, one sincos(phi) per right-hand side
+#endif
         float ts = fmul(fmul(u[1], np_sinf(u[0])), 30.0f);   // f32 product T*sin(delta)*(x_T - x_CG)  (simulator.py:124-125)
         c.torque = (double)ts;
         c.dm = (double)fdiv(-u[1], 3531.6f);                  // simulator.py:126
@@ -296,8 +328,15 @@ struct Sys3 {
         const double Q = (0.5 * 1.225) * v2;
         const double A = (0.3 * Q) * 10.5;
         double sdp, cdp, cp;
+#if RLR_EXACT
         sincos(c.delta + phi, &sdp, &cdp);
         cp = cos(phi);
+#else
+        double sp;
+        sincos_fast(phi, &sp, &cp);
+        sdp = c.sd * cp + c.cd * sp;
+        cdp = c.cd * cp - c.sd * sp;
+#endif
         // NB: drag multiplies cos(phi) on BOTH axes -- reference behaviour (simulator.py:122-123)
         const double Acp = A * cp;
         d[0] = vx; d[1] = vz; d[2] = y[5];
