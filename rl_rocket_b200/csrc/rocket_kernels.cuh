@@ -352,8 +352,14 @@ template <int N>
 RLR_DEV double rms_ratio(const double (&a)[N], const double (&s)[N]) {
     double acc = 0.0;
 #pragma unroll
-    for (int i = 0; i < N; ++i) { double q = RLR_DIV(a[i], s[i]); acc += q * q; }
-    return RLR_DIV(sqrt_(acc), sqrt((double)N));
+#if RLR_EXACT
+    for (int i = 0; i < N; ++i) { double q = a[i] / s[i]; acc += q * q; }
+    return sqrt(acc) / sqrt((double)N);
+#else
+    // step-size-control grade arithmetic (1e-12), see rcp1_ / sqrtc_
+    for (int i = 0; i < N; ++i) { double q = a[i] * rcp1_(s[i]); acc += q * q; }
+    return sqrtc_(acc) * (N == 7 ? 0.37796447300922722721 : 0.26726124191242438468);      // 1 / sqrt(N)
+#endif
 }
 
 // dense-output polynomial row for component i: Q_i[c] = sum_j K[j][i] * P[j][c]
@@ -440,7 +446,11 @@ RLR_DEV int rk45_solve(const typename S::Ctx& c, double t0, double t_bound, doub
         const double d2 = RLR_DIV(rms_ratio<N>(f1, scale), h0);
         double h1;
         if (d1 <= 1e-15 && d2 <= 1e-15) h1 = py_max(1e-6, h0 * 1e-3);
-        else h1 = pow_p02(RLR_DIV(0.01, py_max(d1, d2)));
+#if RLR_EXACT
+        else h1 = pow_p02(0.01 / py_max(d1, d2));
+#else
+        else h1 = powc_p02(0.01 * rcp_(py_max(d1, d2)));
+#endif
         h_abs = py_min(py_min(100 * h0, h1), interval);
     }
     double t = t0;
@@ -482,13 +492,25 @@ RLR_DEV int rk45_solve(const typename S::Ctx& c, double t0, double t_bound, doub
         double acc = 0.0;
 #pragma unroll
         for (int i = 0; i < N; ++i) {
-            const double sc = atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol;
-            const double e = RLR_DIV((((((K[0][i] * E0 + K[2][i] * E2) + K[3][i] * E3) + K[4][i] * E4) + K[5][i] * E5) + K[6][i] * E6) * h, sc);
+            const double num = (((((K[0][i] * E0 + K[2][i] * E2) + K[3][i] * E3) + K[4][i] * E4) + K[5][i] * E5) + K[6][i] * E6) * h;
+#if RLR_EXACT
+            const double e = num / (atol + fmax(fabs(y[i]), fabs(y_new[i])) * rtol);
+#else
+            const double e = num * rcp1_(fma(absmax_(y[i], y_new[i]), rtol, atol));
+#endif
             acc += e * e;
         }
-        const double err = RLR_DIV(sqrt_(acc), sqrt((double)N));
+#if RLR_EXACT
+        const double err = sqrt(acc) / sqrt((double)N);
+#else
+        const double err = sqrtc_(acc) * (N == 7 ? 0.37796447300922722721 : 0.26726124191242438468);
+#endif
         if (err < 1) {
+#if RLR_EXACT
             double factor = (err == 0) ? 10.0 : py_min(10.0, 0.9 * pow_m02(err));
+#else
+            double factor = (err == 0) ? 10.0 : py_min(10.0, 0.9 * powc_m02(err));
+#endif
             if (rejected) factor = py_min(1.0, factor);
             h_abs *= factor;
             // ---- terminal event g(y) = y[EV]  (ivp.py:134-158, 678-699)
@@ -513,7 +535,11 @@ RLR_DEV int rk45_solve(const typename S::Ctx& c, double t0, double t_bound, doub
             min_step = min_step_at(t);
             if (h_abs < min_step) h_abs = min_step;
         } else {
+#if RLR_EXACT
             h_abs *= py_max(0.2, 0.9 * pow(err, -0.2));
+#else
+            h_abs *= py_max(0.2, 0.9 * powc_m02(err));
+#endif
             rejected = true;
         }
     }
