@@ -1284,7 +1284,22 @@ RLR_DEV void env_step(const RlrParams& p, EnvState<S>& st, const float (&u)[3], 
         reward6(p, (const float(&)[14])s, u, a_thr, st.v0, status, res);
     } else {
         const double pi2 = 2.0 * 3.141592653589793;
+#if RLR_EXACT
         st.y[2] = fmod(fmod(st.y[2], pi2) + pi2, pi2);                // simulator.py:77, :150-163
+#else
+        {   // the same two exact remainders without libdevice's fmod: r0 = theta - trunc(theta / 2pi) 2pi is one FMA (exact), the
+            // second operand fl(r0 + 2pi) lies in (0, 4pi), where the remainder is a conditional subtraction
+            const double th = st.y[2];
+            double q = trunc(th * (1.0 / pi2));
+            double r0 = fma(-q, pi2, th);
+            if (r0 <= -pi2 || (th >= 0 && r0 < 0)) r0 += pi2;        // quotient off by one after the rounded multiply
+            else if (r0 >= pi2 || (th < 0 && r0 > 0)) r0 -= pi2;
+            const double s1 = r0 + pi2;
+            double r = (s1 >= pi2) ? s1 - pi2 : s1;
+            if (r >= pi2) r -= pi2;                                   // fl(r0 + 2pi) can round up to exactly 4pi
+            st.y[2] = r;
+        }
+#endif
 #pragma unroll
         for (int i = 0; i < S::N; ++i) { s[i] = (float)st.y[i]; obs[i] = (float)((double)s[i] / p.normalizer[i]); }   // rocket_env.py:155,:175,:209-210
         reward3(p, (const float(&)[7])s, u, a_thr, st.v0, status, res);
