@@ -1175,6 +1175,7 @@ RLR_DEV void reward3(const RlrParams& p, const float (&s)[7], const float* u, fl
         rh0 = 0.0; rh1 = (double)s[1]; vh1 = (double)s[4] - (-1.0); tau = 100.0;
     }
     const double vh0 = (double)s[3];
+#if RLR_EXACT
     const double nr = sqrt(rh0 * rh0 + rh1 * rh1);
     const double nv = sqrt(vh0 * vh0 + vh1 * vh1);
     const double t_go = nr / nv;
@@ -1182,6 +1183,16 @@ RLR_DEV void reward3(const RlrParams& p, const float (&s)[7], const float* u, fl
     const double fac = 1 - exp(-t_go / tau);
     const double mv0 = (double)(-v0);
     const double vt0 = (mv0 * (rh0 / den)) * fac, vt1 = (mv0 * (rh1 / den)) * fac;
+#else
+    const double nr = sqrt_(rh0 * rh0 + rh1 * rh1);
+    const double nv = sqrt_(vh0 * vh0 + vh1 * vh1);
+    const double t_go = nr * rcp_(nv);
+    const double den = py_max(1e-3, nr);
+    const double fac = 1 - exp(-t_go * rcp_(tau));
+    const double mv0 = (double)(-v0);
+    const double iden = rcp_(den);
+    const double vt0 = (mv0 * (rh0 * iden)) * fac, vt1 = (mv0 * (rh1 * iden)) * fac;
+#endif
     const double d0 = (double)s[3] - vt0, d1 = (double)s[4] - vt1;
     o.vt[0] = vt0; o.vt[1] = vt1; o.vt[2] = 0.0; o.vt[3] = t_go;
     const float zeta = fadd(s[2], -1.5707963267948966f);
@@ -1192,7 +1203,11 @@ RLR_DEV void reward3(const RlrParams& p, const float (&s)[7], const float* u, fl
     const float hint_arg = fadd(az, -1.5707963267948966f);
     float hint = hint_arg > 0.0f ? hint_arg : 0.0f;
     if (hint_arg != hint_arg) hint = hint_arg;
+#if RLR_EXACT
     o.terms[0] = p.alfa * sqrt(d0 * d0 + d1 * d1);
+#else
+    o.terms[0] = p.alfa * sqrt_(d0 * d0 + d1 * d1);
+#endif
     o.terms[1] = (double)fmul((float)p.beta, u[1]);
     o.terms[2] = p.eta;
     o.terms[3] = p.gamma * (double)(az > 6.283185307179586f);
