@@ -303,3 +303,20 @@ def test_fast_and_exact_builds_agree_on_every_flag_at_full_size():
           f"{exact.read_stats()['done']} episodes")
     assert dropped <= 2 and int(natt_diff) <= 2
     assert float(worst) <= G.STATE_TOL
+
+
+@pytest.mark.parametrize("math_mode", ["exact", "fast"])
+def test_3dof_65536_envs_one_step_teacher_forced(math_mode):
+    """The 3DOF path at 65 536 envs (batches above 56 832 envs run the 128-register instantiation): every env against the oracle."""
+    N = 65536
+    spec, env, vec = _oracle_pair(3, G.cfg3(), N, 3000, 31, math_mode)
+    assert np.array_equal(env.reset().cpu().numpy(), vec.reset())
+    rng = np.random.RandomState(9)
+    worst = 0.0
+    for t in range(3):
+        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        env.step_tensor(torch.as_tensor(a).cuda())
+        out = vec.step(a)
+        worst = max(worst, _compare_with_oracle(f"3dof 65536 step {t}", spec, env, out))
+        env.y.copy_(torch.as_tensor(vec.y).cuda())
+    print(f"3DOF 65536 one-step [{math_mode}] worst normalised deviation {worst:.3e}")
