@@ -451,6 +451,7 @@ __global__ void __launch_bounds__(BSF) step_kernel_f32(const __grid_constant__ R
                                                        const float* ic_inject, RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed,
                                                        bool stage_obs) {
     extern __shared__ float sKf[];
+    pdl_launch_dependents();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n;
     StepFlags fl = {0, 0, 0, 0, 0, 0};
@@ -459,6 +460,7 @@ __global__ void __launch_bounds__(BSF) step_kernel_f32(const __grid_constant__ R
     EnvStateF st;
     st.episode = 0;
     float obs[14];
+    pdl_wait_for_predecessor();
     if (active) {
         load_state_f(gs, n, i, st);
         float u[3], a_thr;

@@ -57,6 +57,12 @@ RLR_DEV void phase_mark(int k) {
 #define RLR_PHASE(k)
 #endif
 
+// Programmatic dependent launch (sm_90+): a step kernel lets the next kernel of the stream begin launching at once and itself waits
+// for its predecessor's completion only right before its first global access, so consecutive step launches (action repeat, graph
+// replays, random-action loops) overlap the launch latency and block placement of step t+1 with the tail of step t.
+RLR_DEV void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+RLR_DEV void pdl_wait_for_predecessor() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ numpy float32 helpers
 // numpy's SIMD float32 sin/cos for |x| < pi/4 (5-FMA Horner). Explicit fmaf:
 // these FMAs are part of the reference's arithmetic, not a contraction choice.
@@ -1633,6 +1639,7 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
                                                    const float* ic_inject, RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed,
                                                    bool stage_obs) {
     extern __shared__ double sK[];
+    pdl_launch_dependents();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = i < n;
     StepFlags fl = {0, 0, 0, 0, 0, 0};
@@ -1641,6 +1648,7 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
     EnvState<S> st;
     st.episode = 0;
     float obs[S::N];
+    pdl_wait_for_predecessor();
     RLR_PHASE(-1);
     if (active) {
         load_state<S>(gs, n, i, st);
@@ -1823,6 +1831,22 @@ Geometry pick_geometry(Kern kern, int64_t n, int block, size_t smem_min) {
 
 inline int grid_for(int64_t n, int block) { return (int)((n + block - 1) / block); }
 
+// launch with the programmatic-stream-serialization attribute (see pdl_launch_dependents)
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+
 // true when `ptr` is (mapped, pinned) host memory; the answer for the last pointer asked about is cached (one driver query per buffer)
 inline bool is_host_pointer(const void* ptr) {
     static const void* last_ptr = nullptr;
@@ -1850,13 +1874,13 @@ int launch_step(const RlrParams* p, RlrState st, const void* actions, int action
         return (int)cudaGetLastError();
 #endif
         const Geometry g = pick_geometry(step_kernel<Sys6>, n, BS6, SMEM6_BYTES);
-        step_kernel<Sys6><<<grid_for(n, g.block), g.block, g.smem, stream>>>(*p, st, actions, action_kind, ic_inject, out, n, env_offset, seed,
-                                                                            is_host_pointer(out.obs));
+        launch_pdl(step_kernel<Sys6>, grid_for(n, g.block), g.block, g.smem, stream, *p, st, actions, action_kind, ic_inject, out, n, env_offset,
+                   seed, is_host_pointer(out.obs));
     } else {
         if (n > 148 * 3 * 128)
-            step_kernel<Sys3Dense><<<grid_for(n, 128), 128, 0, stream>>>(*p, st, actions, action_kind, ic_inject, out, n, env_offset, seed, false);
+            launch_pdl(step_kernel<Sys3Dense>, grid_for(n, 128), 128, 0, stream, *p, st, actions, action_kind, ic_inject, out, n, env_offset, seed, false);
         else
-            step_kernel<Sys3><<<grid_for(n, 128), 128, 0, stream>>>(*p, st, actions, action_kind, ic_inject, out, n, env_offset, seed, false);
+            launch_pdl(step_kernel<Sys3>, grid_for(n, 128), 128, 0, stream, *p, st, actions, action_kind, ic_inject, out, n, env_offset, seed, false);
     }
     return (int)cudaGetLastError();
 }
@@ -1901,8 +1925,8 @@ int launch_rollout(const RlrParams* p, RlrState st, const void* actions, int act
 // RLR_F32 precision (6DOF only): 128-thread blocks, 27 KB of dynamic shared memory for the binary32 stage matrix
 int launch_step_f32(const RlrParams* p, RlrState st, const void* actions, int action_kind, const float* ic_inject, RlrStepOut out, int64_t n,
                     int64_t env_offset, uint64_t seed, cudaStream_t stream) {
-    f32::step_kernel_f32<<<grid_for(n, f32::BSF), f32::BSF, f32::SMEMF_BYTES, stream>>>(*p, st, (const float*)actions, action_kind, ic_inject, out,
-                                                                                         n, env_offset, seed, is_host_pointer(out.obs));
+    launch_pdl(f32::step_kernel_f32, grid_for(n, f32::BSF), f32::BSF, f32::SMEMF_BYTES, stream, *p, st, (const float*)actions, action_kind, ic_inject,
+               out, n, env_offset, seed, is_host_pointer(out.obs));
     return (int)cudaGetLastError();
 }
 int launch_reset_f32(const RlrParams* p, RlrState st, const uint8_t* mask, const float* ic_inject, float* obs, int64_t n, int64_t env_offset,
