@@ -12,8 +12,12 @@
  *                  Rocket.step       my_environment/envs/rocket_env.py:150-175   -> Simulator3DOF.step utils/simulator.py:55-86
  *                  + gym TimeLimit.step / SB3 DummyVecEnv.step_wait semantics (main_6DOF.py:21-22,71; main.py:65-70,105)
  *                  + wrappers DiscreteActions3DOF / RewardAnnealing (my_environment/wrappers/wrappers.py:24-35,68-86)
+ *   rlr_step_range the same step restricted to the environments [begin, begin + count) of the batch (sub-batch pipelining:
+ *                  several ranges on different streams, so one range's PCIe transfers overlap another's integration)
  *   rlr_rollout    T consecutive rlr_step calls fused in one launch (state stays in registers)
- *   rlr_stats_*    the per-episode bookkeeping SB3's Monitor does on the host (main.py:65-70)
+ *   RlrStepOut.stats / fin_ret / fin_len   the per-episode bookkeeping SB3's Monitor does on the host (main.py:65-70),
+ *                  accumulated on the device by the step / rollout kernels (there is no separate statistics entry point)
+ *   RlrParams.obs_mode = RLR_OBS_GAUDET    the GaudetStateObs observation wrapper (my_environment/wrappers/wrappers.py:51-66)
  *
  * Conventions
  *   - Every function returns 0 on success or a negative RLR_E_* code; rlr_last_error() gives a
@@ -34,7 +38,7 @@
 extern "C" {
 #endif
 
-#define RLR_ABI_VERSION 2
+#define RLR_ABI_VERSION 3
 #define RLR_NMAX 14          /* state components: 14 (6DOF), 7 (3DOF / 1DOF) */
 #define RLR_MAX_DISCRETE 16
 
@@ -51,6 +55,14 @@ enum {
 enum {
     RLR_MATH_EXACT = 0,      /* IEEE op-for-op sequence of the reference (no FMA contraction, true divisions) */
     RLR_MATH_FAST  = 1       /* FMA contraction + reciprocal multiplies; deviation bounded in tests (<= 1e-9 normalised) */
+};
+
+/* obs_mode */
+enum {
+    RLR_OBS_STATE  = 0,      /* normalised state (rocket_env.py:963-964 / :209-210); 1DOF: (z, vz) */
+    RLR_OBS_GAUDET = 1       /* 3DOF only: f32 [vx - vtarg_x, vz - vtarg_z, t_go, z] of the PHYSICAL state -- GaudetStateObs
+                                (wrappers.py:51-66) with its two defects fixed: it calls the existing _compute_vtarg
+                                (rocket_env.py:219-247) and feeds it the un-normalised r, v the method is written for */
 };
 
 /* precision of the integrated state */
@@ -76,6 +88,10 @@ typedef struct RlrParams {
     float   max_thrust;
     int32_t n_discrete;
     float   discrete_table[2 * RLR_MAX_DISCRETE];  /* physical (gimbal, thrust) pairs */
+    float   discrete_thr[RLR_MAX_DISCRETE];        /* the rows' normalised throttle (row[1], an integer in the reference's table): what
+                                                      RewardAnnealing sees under DiscreteActions3DOF, -xi * (row[1] + 1) in float64 */
+    int32_t obs_mode;                              /* RLR_OBS_* */
+    int32_t reserved0;
 } RlrParams;
 
 /* Persistent per-environment state (device pointers, caller-owned). */
@@ -136,6 +152,13 @@ int rlr_reset(const RlrParams* p, int precision, RlrState st, const uint8_t* mas
 /* one environment step for n environments, TimeLimit + auto-reset fused */
 int rlr_step(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind,
              const float* ic_inject, RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed, void* stream);
+
+/* rlr_step for the environments [begin, begin + count) only; every per-environment pointer (state, actions, outputs) is still
+ * indexed by the absolute environment index and n stays the batch size (the structure-of-arrays stride).  Ranges are independent:
+ * launch them on different streams to pipeline one range's host transfers behind another's integration. */
+int rlr_step_range(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind,
+                   const float* ic_inject, RlrStepOut out, int64_t n, int64_t begin, int64_t count, int64_t env_offset,
+                   uint64_t seed, void* stream);
 
 /* T fused steps.  actions: [T][n][nact] (or i64 [T][n] for discrete).  Outputs, when non-NULL, are
  * [T][n][...] rollout buffers (obs/reward/done/truncated) -- the layout SB3's RolloutBuffer uses. */

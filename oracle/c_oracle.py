@@ -36,6 +36,8 @@ def nact(p):
 
 
 def nobs(p):
+    if p.dof == 3 and p.obs_mode == 1:
+        return 4
     return 2 if p.dof == 1 else ndim(p)
 
 
@@ -97,8 +99,13 @@ class VecOracle:
         self.episode = np.zeros(self.N, np.int32)
         self.v0 = np.zeros(self.N, np.float32)
         self.ep_ret = np.zeros(self.N)
+        self._started = False
 
     def reset(self, ic=None):
+        """First reset: ICs keyed by the current episode indices; later explicit resets advance them first (fresh ICs)."""
+        if self._started:
+            self.episode += 1
+        self._started = True
         obs = np.zeros((self.N, nobs(self.p)), np.float32)
         if ic is not None:
             ic = np.ascontiguousarray(ic, dtype=np.float32)

@@ -54,6 +54,7 @@ typedef struct {
     double att_traj_limit[3], att_land_limit[3], omega_lim[3];
     double max_gimbal;          /* deg2rad(20) */
     float  max_thrust;          /* 981e3 */
+    int    obs_mode;            /* 0 normalised state; 1 (3DOF) GaudetStateObs, corrected (wrappers.py:51-66): see gaudet_obs3 */
 } OrParams;
 
 /* ------------------------------------------------------------ small helpers */
@@ -74,8 +75,33 @@ static float np_cosf_small(float x) {        /* numpy f32 cos, |x| < pi/4 */
     r = fmaf(r, x2, 1.0f);
     return r;
 }
-static float np_sinf(float x) { return fabsf(x) < 0.78539816f ? np_sinf_small(x) : (float)sin((double)x); }
-static float np_cosf(float x) { return fabsf(x) < 0.78539816f ? np_cosf_small(x) : (float)cos((double)x); }
+/* numpy's float32 sin / cos ufunc loops for any |x| up to the Cody-Waite limit (numpy/_core/src/umath/
+ * loops_trigonometric.dispatch: cos 71476.0625, sin 117435.992; call sites simulator.py:351-357, :124):
+ *   quadrant  k = rint(x * 2/pi) via the 1.5 * 2^23 magic-number add -- the multiply-add is FUSED
+ *   reduction r = fma(k, -pi/2_c, ...) in three f32 terms
+ *   both polynomials on r, pick sin or cos by the parity of k (k + 1 for cosine), negate when bit 1 is set.
+ * For |x| < pi/4, k = 0 and r = x: the small-argument polynomials above.  Checked in this image against
+ * np.sin / np.cos on EVERY float32 with |x| <= 64 (2.2e9 arguments per function, 0 mismatches) and on 8e6
+ * random arguments up to +-7e4; tests/test_oracle_golden.py re-checks samples.  Beyond the limit numpy
+ * calls libm per element; restated as the correctly rounded double function (not pinned, unreachable
+ * for |action| < 2e5). */
+static float np_sincosf(float x, int want_cos) {
+    const float lim = want_cos ? 71476.0625f : 117435.992f;
+    if (!(fabsf(x) <= lim)) return want_cos ? (float)cos((double)x) : (float)sin((double)x);
+    const float magic = 0x1.8p23f;
+    volatile float t = fmaf(x, 0.636619772367581343075535053490057448f, magic);
+    const float k = t - magic;
+    float r = fmaf(k, -0x1.921fb0p+00f, x);
+    r = fmaf(k, -0x1.5110b4p-22f, r);
+    r = fmaf(k, -0x1.846988p-48f, r);
+    int ik = (int)k;
+    if (want_cos) ik += 1;
+    float v = ((ik & 1) == 0) ? np_sinf_small(r) : np_cosf_small(r);
+    if ((ik & 2) == 2) v = 0.0f - v;
+    return v;
+}
+static float np_sinf(float x) { return np_sincosf(x, 0); }
+static float np_cosf(float x) { return np_sincosf(x, 1); }
 
 /* numpy float32 linalg.norm on a short vector: sdot with a double accumulator of
  * f32-rounded products, result rounded to f32, then sqrtf (SURVEY "hard parts"). */
@@ -367,6 +393,13 @@ static void denorm_action3(const OrParams* p, const float* a, float* u) {
     u[1] = ((a[1] + 1.0f) / 2.0f) * p->max_thrust;
 }
 
+/* DiscreteActions3DOF.action (wrappers.py:34): the table row is an int64 ndarray, so Rocket._denormalize_action
+ * (rocket_env.py:395-406) runs in float64 and only the final np.float32([...]) rounds.  `row` holds the integers as floats. */
+static void denorm_action3_row(const OrParams* p, const float* row, float* u) {
+    u[0] = (float)((double)row[0] * p->max_gimbal);
+    u[1] = (float)((((double)row[1] + 1.0) / 2.0) * (double)p->max_thrust);
+}
+
 /* ------------------------------------------------------- simulators */
 static double t_of_k(const OrParams* p, int k) { return (double)((int64_t)k * p->dt_ms) / 1000.0; }
 
@@ -482,7 +515,8 @@ static void reward6(const OrParams* p, const float* s, const float* u, const flo
     o->done = (status != 0) || viol;
 }
 
-static void reward3(const OrParams* p, const float* s, const float* u, const float* a_norm, float v0, int status, StepOut* o) {
+/* Rocket._compute_vtarg (rocket_env.py:219-247) on the f32 state */
+static void vtarg3(const OrParams* p, const float* s, float v0, double* vt, double* t_go_out) {
     double rh[2], vh[2], tau;
     if ((double)s[1] > p->waypoint) {
         rh[0] = (double)s[0] - 0; rh[1] = (double)s[1] - p->waypoint;
@@ -496,8 +530,28 @@ static void reward3(const OrParams* p, const float* s, const float* u, const flo
     double den = py_max(1e-3, nr);
     double fac = 1 - exp(-t_go / tau);
     double mv0 = (double)(-v0);
-    double vt[2], dv[2];
-    for (int i = 0; i < 2; ++i) { vt[i] = (mv0 * (rh[i] / den)) * fac; dv[i] = (double)s[3 + i] - vt[i]; o->vtarg[i] = vt[i]; }
+    for (int i = 0; i < 2; ++i) vt[i] = (mv0 * (rh[i] / den)) * fac;
+    *t_go_out = t_go;
+}
+
+/* GaudetStateObs.observation (wrappers.py:55-66) with its two defects fixed -- it calls `compute_vtarg`, which does not exist
+ * (the method is `_compute_vtarg`, rocket_env.py:219), and passes it the NORMALISED r, v although the method is written for
+ * the physical state (waypoint in metres, v_0 in m/s).  Fixed semantics: np.float32([vx - vt_x, vz - vt_z, t_go, z]) of the
+ * physical float32 state the environment itself hands to _compute_vtarg (rocket_env.py:155, :180-184).  Pinned by
+ * tests/golden/traj_3dof_gaudet.npz, generated with that corrected wrapper over the live reference env. */
+static void gaudet_obs3(const OrParams* p, const float* s, float v0, float* obs) {
+    double vt[2], t_go;
+    vtarg3(p, s, v0, vt, &t_go);
+    obs[0] = (float)((double)s[3] - vt[0]);
+    obs[1] = (float)((double)s[4] - vt[1]);
+    obs[2] = (float)t_go;
+    obs[3] = s[1];
+}
+
+static void reward3(const OrParams* p, const float* s, const float* u, const float* a_norm, int a_is_row, float v0, int status, StepOut* o) {
+    double vt[2], dv[2], t_go;
+    vtarg3(p, s, v0, vt, &t_go);
+    for (int i = 0; i < 2; ++i) { dv[i] = (double)s[3 + i] - vt[i]; o->vtarg[i] = vt[i]; }
     o->vtarg[2] = 0; o->t_go = t_go;
     float zeta = s[2] - 1.5707963267948966f;        /* f32 scalar - python float -> f32 */
     float az = fabsf(zeta);
@@ -518,10 +572,17 @@ static void reward3(const OrParams* p, const float* s, const float* u, const flo
     if (viol) r += -50;
     if (p->reward_mode == 1) {
         /* 3DOF: python float (ac + rg) + np.float32 -> f32 arithmetic */
-        float tp = (float)(-p->xi) * (a_norm[1] + 1.0f);
-        float rr = (float)(o->terms[3] + o->terms[5]) + tp;
-        r = (double)rr;
-        o->terms[1] = (double)tp;
+        if (a_is_row) {
+            /* DiscreteActions3DOF(RewardAnnealing(env)): the wrapper sees the int64 table row -> -xi * (row[1] + 1) in float64 */
+            double tp = (-p->xi) * ((double)a_norm[1] + 1.0);
+            r = (o->terms[3] + o->terms[5]) + tp;
+            o->terms[1] = tp;
+        } else {
+            float tp = (float)(-p->xi) * (a_norm[1] + 1.0f);
+            float rr = (float)(o->terms[3] + o->terms[5]) + tp;
+            r = (double)rr;
+            o->terms[1] = (double)tp;
+        }
     }
     o->reward = r; o->viol = viol; o->landed = landed; o->status = status;
     o->done = (status != 0) || viol;
@@ -568,10 +629,12 @@ void or_reset_from_ic(const OrParams* p, const float* ic_in, double* y, float* v
         *v0 = f32_norm(ic + 3, 2);
     }
     for (int i = 0; i < n; ++i) { y[i] = (double)ic[i]; obs[i] = (float)((double)ic[i] / p->normalizer[i]); }
+    if (p->dof == 3 && p->obs_mode == 1) gaudet_obs3(p, ic, *v0, obs);      /* ObservationWrapper.reset -> observation() */
 }
 
 /* One environment step WITHOUT TimeLimit / auto-reset.
- *  action_kind 0: normalised f32 action (3 / 2 / 1 components); 1: physical f32 u (3 / 2).
+ *  action_kind 0: normalised f32 action (3 / 2 / 1 components); 1: physical f32 u (3 / 2);
+ *              2: (3DOF) a DiscreteActions3DOF table row [gimbal, throttle] given as floats holding the table's integers.
  *  y in/out (f64), k = episode step index before this step.
  *  outputs: obs f32[n] (6DOF: (float)(y/norm); 3DOF: (float)((double)s_f32/norm)); out->* */
 void or_env_step(const OrParams* p, double* y, int k, float v0, const float* action, int action_kind,
@@ -593,12 +656,14 @@ void or_env_step(const OrParams* p, double* y, int k, float v0, const float* act
         float u[2], a2[2];
         if (p->dof == 1) { a2[0] = 0.0f; a2[1] = action[0]; } else { a2[0] = action[0]; a2[1] = action[1]; }
         if (action_kind == 0) { denorm_action3(p, a2, u); a_norm[0] = a2[0]; a_norm[1] = a2[1]; }
+        else if (action_kind == 2) { denorm_action3_row(p, a2, u); a_norm[0] = a2[0]; a_norm[1] = a2[1]; }
         else { u[0] = a2[0]; u[1] = a2[1]; }
         int st = sim3_step(p, y, k, u, &nfev, &natt);
         float s[7];
         for (int i = 0; i < 7; ++i) s[i] = (float)y[i];
-        reward3(p, s, u, a_norm, v0, st, &o);
+        reward3(p, s, u, a_norm, action_kind == 2, v0, st, &o);
         for (int i = 0; i < 7; ++i) obs[i] = (float)((double)s[i] / p->normalizer[i]);
+        if (p->dof == 3 && p->obs_mode == 1) gaudet_obs3(p, s, v0, obs);
     }
     *reward = o.reward;
     if (terms) memcpy(terms, o.terms, sizeof(o.terms));
@@ -616,7 +681,7 @@ void or_vec_step(const OrParams* p, int64_t N, int64_t env_offset, uint64_t seed
                  double* fin_ret, int32_t* fin_len, uint8_t* fin_landed, int32_t* natt_out, double* y_pre_reset) {
     int n = (p->dof == 6) ? 14 : 7;
     int na = (p->dof == 6) ? 3 : (p->dof == 3 ? 2 : 1);
-    int no = (p->dof == 1) ? 2 : n;
+    int no = (p->dof == 1) ? 2 : ((p->dof == 3 && p->obs_mode == 1) ? 4 : n);
     for (int64_t i = 0; i < N; ++i) {
         double yy[NMAX]; float ob[NMAX]; double r; int fl[6];
         for (int c = 0; c < n; ++c) yy[c] = y[c * N + i];
@@ -654,7 +719,7 @@ void or_vec_reset(const OrParams* p, int64_t N, int64_t env_offset, uint64_t see
                   double* y, int32_t* k, int32_t* episode, float* v0, double* ep_ret,
                   const float* ic_inject, float* obs) {
     int n = (p->dof == 6) ? 14 : 7;
-    int no = (p->dof == 1) ? 2 : n;
+    int no = (p->dof == 1) ? 2 : ((p->dof == 3 && p->obs_mode == 1) ? 4 : n);
     for (int64_t i = 0; i < N; ++i) {
         float ic[NMAX], ob[NMAX]; double yy[NMAX];
         if (ic_inject) memcpy(ic, ic_inject + i * n, sizeof(float) * n);

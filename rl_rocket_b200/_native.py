@@ -11,10 +11,11 @@ MAX_DISCRETE = 16
 NSTATS = 8
 STAT_NAMES = ("steps", "attempts", "done", "landed", "viol", "trunc", "len_sum", "ret_sum_fx")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 ACT_NORMALIZED, ACT_PHYSICAL, ACT_DISCRETE = 0, 1, 2
 MATH_EXACT, MATH_FAST = 0, 1
 F64, F32 = 0, 1
+OBS_STATE, OBS_GAUDET = 0, 1
 
 LIB_PATH = os.environ.get("RLR_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "_C", "librlrocket.so")   # RLR_LIB: tuning builds only
 
@@ -34,6 +35,7 @@ class RlrParams(C.Structure):
         ("att_traj_c", C.c_double * 3), ("att_land_c", C.c_double * 3),
         ("max_gimbal", C.c_double), ("max_thrust", C.c_float),
         ("n_discrete", C.c_int32), ("discrete_table", C.c_float * (2 * MAX_DISCRETE)),
+        ("discrete_thr", C.c_float * MAX_DISCRETE), ("obs_mode", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -47,7 +49,7 @@ class RlrStepOut(C.Structure):
 
 
 EXPORTS = ("rlr_abi_version", "rlr_last_error", "rlr_sizeof_params", "rlr_ndim", "rlr_nact", "rlr_nobs",
-           "rlr_reset", "rlr_step", "rlr_rollout", "rlr_fma_peak")
+           "rlr_reset", "rlr_step", "rlr_step_range", "rlr_rollout", "rlr_fma_peak")
 
 _lib = None
 
@@ -74,6 +76,8 @@ def load():
     lib.rlr_reset.argtypes = [P, C.c_int, RlrState, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p]
     lib.rlr_step.argtypes = [P, C.c_int, C.c_int, RlrState, C.c_void_p, C.c_int, C.c_void_p, RlrStepOut, C.c_int64, C.c_int64,
                              C.c_uint64, C.c_void_p]
+    lib.rlr_step_range.argtypes = [P, C.c_int, C.c_int, RlrState, C.c_void_p, C.c_int, C.c_void_p, RlrStepOut, C.c_int64, C.c_int64, C.c_int64,
+                                   C.c_int64, C.c_uint64, C.c_void_p]
     lib.rlr_rollout.argtypes = [P, C.c_int, C.c_int, RlrState, C.c_void_p, C.c_int, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p]
     lib.rlr_fma_peak.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]

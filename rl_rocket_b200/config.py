@@ -59,7 +59,7 @@ class EnvSpec:
     """Everything derived from the constructor kwargs: the kernel POD plus the host-side arrays."""
 
     def __init__(self, dof, IC=None, ICRange=None, timestep=None, seed=None, reward_coeff=None, trajectory_limits=None,
-                 landing_params=None, max_episode_steps=0, reward_mode=0, discrete_table=None):
+                 landing_params=None, max_episode_steps=0, reward_mode=0, discrete_table=None, obs_mode=0):
         if dof not in (6, 3, 1):
             raise ValueError("dof must be 6, 3 or 1")
         d = DEFAULTS_6DOF if dof == 6 else DEFAULTS_3DOF
@@ -73,9 +73,12 @@ class EnvSpec:
         self.landing_params = DEFAULTS_6DOF["landing_params"] if landing_params is None else landing_params
         self.max_episode_steps = int(max_episode_steps or 0)
         self.reward_mode = int(reward_mode)
+        self.obs_mode = {0: 0, 1: 1, "state": 0, "gaudet": 1}[obs_mode]
+        if self.obs_mode == 1 and dof != 3:
+            raise ValueError("obs_mode='gaudet' (GaudetStateObs, wrappers.py:51-66) is defined for the 3DOF environment")
         self.ndim = 14 if dof == 6 else 7
         self.nact = {6: 3, 3: 2, 1: 1}[dof]
-        self.nobs = 2 if dof == 1 else self.ndim
+        self.nobs = 2 if dof == 1 else (4 if self.obs_mode == 1 else self.ndim)
         if len(self.IC) != self.ndim or len(self.ICRange) != self.ndim:
             raise ValueError(f"IC and ICRange must have {self.ndim} elements")
 
@@ -90,9 +93,11 @@ class EnvSpec:
         else:
             self._derive_3dof()
         self.discrete_table = None
+        self.discrete_rows = None
+        self.params = RlrParams()        # ONE struct for the life of the spec: batches keep a byref to it, so updates are in place
         if discrete_table is not None:
             self.set_discrete_table(discrete_table)
-        self.params = self._pack()
+        self._pack()
 
     # rocket_env.py:575-620
     def _derive_6dof(self):
@@ -136,12 +141,21 @@ class EnvSpec:
             raise ValueError(f"discrete table must be [n<= {MAX_DISCRETE}][2]")
         phys = [np.float32([r[0] * self.max_gimbal, (r[1] + 1) / 2.0 * self.max_thrust]) for r in rows]
         self.discrete_table = np.stack(phys).astype(np.float32)
-        if hasattr(self, "params"):
-            self.params = self._pack()
+        self.discrete_rows = np.array(rows, dtype=np.float32)      # the normalised rows: RewardAnnealing sees row[1] (wrappers.py:80)
+        if hasattr(self, "state_normalizer"):
+            self._pack()
+
+    def set_reward_mode(self, reward_mode):
+        """Switch between the shaped reward (0) and RewardAnnealing (1) in place (main_6DOF.py:95-103): every batch built on this
+        spec sees the change at its next step."""
+        self.reward_mode = int(reward_mode)
+        self.params.reward_mode = self.reward_mode
 
     def _pack(self):
-        p = RlrParams()
+        """(Re)fill self.params IN PLACE (batches hold a pointer to it)."""
+        p = self.params
         p.dof, p.reward_mode, p.max_episode_steps = self.dof, self.reward_mode, self.max_episode_steps
+        p.obs_mode = self.obs_mode
         p.dt = float(self.timestep)
         p.dt_ms = timestep_ms(self.timestep)
         rc = self.reward_coeff
@@ -174,6 +188,8 @@ class EnvSpec:
             flat = self.discrete_table.reshape(-1)
             for i, v in enumerate(flat):
                 p.discrete_table[i] = float(v)
+            for i, r in enumerate(self.discrete_rows):
+                p.discrete_thr[i] = float(r[1])
         return p
 
     def with_(self, **changes):
@@ -181,10 +197,45 @@ class EnvSpec:
         kw = dict(dof=self.dof, IC=self.IC, ICRange=self.ICRange, timestep=self.timestep, seed=self.seed,
                   reward_coeff=self.reward_coeff, trajectory_limits=self.trajectory_limits, landing_params=self.landing_params,
                   max_episode_steps=self.max_episode_steps, reward_mode=self.reward_mode,
-                  discrete_table=None)
+                  discrete_table=None, obs_mode=self.obs_mode)
         kw.update(changes)
         spec = EnvSpec(**kw)
         if self.discrete_table is not None and "discrete_table" not in changes:
             spec.discrete_table = self.discrete_table.copy()
-            spec.params = spec._pack()
+            spec.discrete_rows = self.discrete_rows.copy()
+            spec._pack()
         return spec
+
+
+# ---------------------------------------------------------------------------------------------- canonical configurations
+def env_config_6dof():
+    """`env_config` of the reference's configuration_file.py:4-34 (BASELINE configs 3, 4, 5)."""
+    pi = np.pi
+    return {
+        "timestep": 0.1, "seed": 42,
+        "IC": [500, 100, 100, -50, 0, 0, 1, 0, 0, 0, 0, 0, 0, 45e3],
+        "ICRange": [50, 10, 10, 10, 10, 10, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 1e3],
+        "reward_coeff": {"alfa": -0.01, "beta": -1e-7, "delta": -5, "eta": 0.05, "gamma": -10, "kappa": 10, "xi": 0.004},
+        "trajectory_limits": {"attitude_limit": [1.5, 1.5, 2 * pi]},
+        "landing_params": {"waypoint": 50, "landing_radius": 30, "maximum_velocity": 10,
+                           "landing_attitude_limit": [10 / 180 * pi, 10 / 180 * pi, 2 * pi], "omega_lim": [0.2, 0.2, 0.2]},
+    }
+
+
+def env_config_3dof():
+    """`config` of the reference's main.py:23-43 as main.py:48-56 passes it to the Rocket constructor (BASELINE config 2)."""
+    pi = np.pi
+    return {
+        "IC": [-1600, 2000, pi * 3 / 4, 180, -90, 0, 50e3], "ICRange": [5, 50, 0, 0, 0, 0, 1e3], "timestep": 0.05, "seed": 42,
+        "reward_coeff": {"alfa": -0.01, "beta": 0, "delta": -5, "eta": 0.2, "gamma": -10, "kappa": 10, "xi": 0.004,
+                         "waypoint": 30, "landing_radius": 30},
+    }
+
+
+def env_config_1dof():
+    """BASELINE config 1: the main.py configuration restricted to the vertical (README.md:4-8)."""
+    return dict(IC=[0, 2000, np.pi / 2, 0, -90, 0, 50e3], ICRange=[0, 50, 0, 0, 0, 0, 1e3], timestep=0.05, seed=42,
+                reward_coeff=env_config_3dof()["reward_coeff"])
+
+
+MAX_EPISODE_STEPS = {6: 800, 3: 3000, 1: 3000}      # configuration_file.py:37,44 (80 s / 0.1 s); main.py:28,45 (150 s / 0.05 s)

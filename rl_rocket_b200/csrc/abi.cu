@@ -8,7 +8,8 @@
 
 #define RLR_DECLARE_LAUNCHERS(NS)                                                                                                          \
     namespace NS {                                                                                                                         \
-    int launch_step(const RlrParams*, RlrState, const void*, int, const float*, RlrStepOut, int64_t, int64_t, uint64_t, cudaStream_t);    \
+    int launch_step(const RlrParams*, RlrState, const void*, int, const float*, RlrStepOut, int64_t, int64_t, int64_t, int64_t, uint64_t,   \
+                    cudaStream_t);                                                                                                          \
     int launch_reset(const RlrParams*, RlrState, const uint8_t*, const float*, float*, int64_t, int64_t, uint64_t, cudaStream_t);         \
     int launch_rollout(const RlrParams*, RlrState, const void*, int, int, float*, float*, uint8_t*, uint8_t*, float*, unsigned long long*, \
                        int64_t, int64_t, uint64_t, cudaStream_t);                                                                          \
@@ -17,7 +18,8 @@ RLR_DECLARE_LAUNCHERS(rlr_exact)
 RLR_DECLARE_LAUNCHERS(rlr_fast)
 
 namespace rlr_fast {      // RLR_F32 precision (6DOF, fast math only)
-int launch_step_f32(const RlrParams*, RlrState, const void*, int, const float*, RlrStepOut, int64_t, int64_t, uint64_t, cudaStream_t);
+int launch_step_f32(const RlrParams*, RlrState, const void*, int, const float*, RlrStepOut, int64_t, int64_t, int64_t, int64_t, uint64_t,
+                    cudaStream_t);
 int launch_reset_f32(const RlrParams*, RlrState, const uint8_t*, const float*, float*, int64_t, int64_t, uint64_t, cudaStream_t);
 int launch_rollout_f32(const RlrParams*, RlrState, const void*, int, int, float*, float*, uint8_t*, uint8_t*, float*, unsigned long long*,
                        int64_t, int64_t, uint64_t, cudaStream_t);
@@ -43,6 +45,8 @@ static int check_params(const RlrParams* p) {
     if (p->dof != 6 && p->dof != 3 && p->dof != 1) return fail(RLR_E_INVALID, "dof must be 6, 3 or 1");
     if (p->dt_ms <= 0 || !(p->dt > 0)) return fail(RLR_E_INVALID, "timestep must be a positive whole number of milliseconds");
     if (p->n_discrete < 0 || p->n_discrete > RLR_MAX_DISCRETE) return fail(RLR_E_INVALID, "n_discrete out of range");
+    if (p->obs_mode != RLR_OBS_STATE && p->obs_mode != RLR_OBS_GAUDET) return fail(RLR_E_INVALID, "bad obs_mode");
+    if (p->obs_mode == RLR_OBS_GAUDET && p->dof != 3) return fail(RLR_E_UNSUPPORTED, "RLR_OBS_GAUDET is defined for the 3DOF environment (wrappers.py:52)");
     return RLR_OK;
 }
 static int check_precision(const RlrParams* p, int precision, int math_mode) {
@@ -64,7 +68,7 @@ const char* rlr_last_error(void) { return g_err; }
 int rlr_sizeof_params(void) { return (int)sizeof(RlrParams); }
 int rlr_ndim(const RlrParams* p) { return p->dof == 6 ? 14 : 7; }
 int rlr_nact(const RlrParams* p) { return p->dof == 6 ? 3 : (p->dof == 3 ? 2 : 1); }
-int rlr_nobs(const RlrParams* p) { return p->dof == 6 ? 14 : (p->dof == 3 ? 7 : 2); }
+int rlr_nobs(const RlrParams* p) { return p->dof == 6 ? 14 : (p->dof == 3 ? (p->obs_mode == RLR_OBS_GAUDET ? 4 : 7) : 2); }
 
 int rlr_reset(const RlrParams* p, int precision, RlrState st, const uint8_t* mask, const float* ic_inject, float* obs, int64_t n,
               int64_t env_offset, uint64_t seed, void* stream) {
@@ -78,12 +82,12 @@ int rlr_reset(const RlrParams* p, int precision, RlrState st, const uint8_t* mas
     return cuda_status(rlr_exact::launch_reset(p, st, mask, ic_inject, obs, n, env_offset, seed, (cudaStream_t)stream));
 }
 
-int rlr_step(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind, const float* ic_inject,
-             RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed, void* stream) {
+int rlr_step_range(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind, const float* ic_inject,
+                   RlrStepOut out, int64_t n, int64_t begin, int64_t count, int64_t env_offset, uint64_t seed, void* stream) {
     int rc = check_params(p);
     if (rc) return rc;
-    if (n < 0) return fail(RLR_E_INVALID, "n < 0");
-    if (n == 0) return RLR_OK;
+    if (n < 0 || begin < 0 || count < 0 || begin + count > n) return fail(RLR_E_INVALID, "need 0 <= begin, 0 <= count, begin + count <= n");
+    if (count == 0) return RLR_OK;            /* empty batch / empty range: nothing to do (zero-size buffers may be NULL) */
     if ((rc = check_state(st))) return rc;
     if ((rc = check_precision(p, precision, math_mode))) return rc;
     if (!actions || !out.obs || !out.done) return fail(RLR_E_INVALID, "actions, out.obs and out.done are required");
@@ -91,10 +95,19 @@ int rlr_step(const RlrParams* p, int precision, int math_mode, RlrState st, cons
     if (action_kind == RLR_ACT_DISCRETE && (p->dof != 3 || p->n_discrete <= 0))
         return fail(RLR_E_INVALID, "discrete actions need dof == 3 and a discrete_table");
     cudaStream_t s = (cudaStream_t)stream;
-    if (precision == RLR_F32) return cuda_status(rlr_fast::launch_step_f32(p, st, actions, action_kind, ic_inject, out, n, env_offset, seed, s));
-    if (math_mode == RLR_MATH_EXACT) return cuda_status(rlr_exact::launch_step(p, st, actions, action_kind, ic_inject, out, n, env_offset, seed, s));
-    if (math_mode == RLR_MATH_FAST) return cuda_status(rlr_fast::launch_step(p, st, actions, action_kind, ic_inject, out, n, env_offset, seed, s));
+    if (precision == RLR_F32)
+        return cuda_status(rlr_fast::launch_step_f32(p, st, actions, action_kind, ic_inject, out, n, begin, count, env_offset, seed, s));
+    if (math_mode == RLR_MATH_EXACT)
+        return cuda_status(rlr_exact::launch_step(p, st, actions, action_kind, ic_inject, out, n, begin, count, env_offset, seed, s));
+    if (math_mode == RLR_MATH_FAST)
+        return cuda_status(rlr_fast::launch_step(p, st, actions, action_kind, ic_inject, out, n, begin, count, env_offset, seed, s));
     return fail(RLR_E_INVALID, "bad math_mode");
+}
+
+int rlr_step(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind, const float* ic_inject,
+             RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed, void* stream) {
+    if (n < 0) return fail(RLR_E_INVALID, "n < 0");
+    return rlr_step_range(p, precision, math_mode, st, actions, action_kind, ic_inject, out, n, 0, n, env_offset, seed, stream);
 }
 
 int rlr_rollout(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind, int32_t T, float* obs_buf,

@@ -193,6 +193,7 @@ RLR_DEV int rk45_solve6f(const Ctx6f& c, float dt, float (&y)[14], int& natt, fl
         kf_store(sKb, 0, kk);
     }
     natt = 0;
+    if (y[13] == 0.0f) { natt = 1; return -1; }        // zero mass: scipy's outcome stated directly (see rk45_solve6)
     // state component of stage-matrix slot cc: 3 + cc for cc < 7 (v, q), 4 + cc for cc = 7, 8 (w_y, w_z)
 #define YIDX(cc) ((cc) < 7 ? 3 + (cc) : 4 + (cc))
     float h_abs;
@@ -448,12 +449,12 @@ RLR_DEV void write_obs6_warp_f(const RlrParams& p, float* dst, int64_t i, bool a
 }
 
 __global__ void __launch_bounds__(BSF) step_kernel_f32(const __grid_constant__ RlrParams p, RlrState gs, const float* actions, int action_kind,
-                                                       const float* ic_inject, RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed,
-                                                       bool stage_obs) {
+                                                       const float* ic_inject, RlrStepOut out, int64_t n, int64_t i_begin, int64_t i_end,
+                                                       int64_t env_offset, uint64_t seed, bool stage_obs) {
     extern __shared__ float sKf[];
     pdl_launch_dependents();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < n;
+    const int64_t i = i_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < i_end;
     StepFlags fl = {0, 0, 0, 0, 0, 0};
     int ep_len = 0;
     double ep_ret = 0.0;
@@ -464,7 +465,8 @@ __global__ void __launch_bounds__(BSF) step_kernel_f32(const __grid_constant__ R
     if (active) {
         load_state_f(gs, n, i, st);
         float u[3], a_thr;
-        map_action<Sys6>(p, actions, action_kind, i, u, a_thr);
+        bool thr_is_row;
+        map_action<Sys6>(p, actions, action_kind, i, u, a_thr, thr_is_row);
         StepRes res;
         env_step_f(p, st, u, a_thr, obs, res, fl, sKf);
         ep_len = st.k; ep_ret = st.ep_ret;
@@ -547,7 +549,8 @@ __global__ void __launch_bounds__(BSF) rollout_kernel_f32(const __grid_constant_
         double ep_ret = 0.0;
         if (active) {
             float u[3], a_thr;
-            map_action<Sys6>(p, actions + (int64_t)t * n * 3, action_kind, i, u, a_thr);
+            bool thr_is_row;
+            map_action<Sys6>(p, actions + (int64_t)t * n * 3, action_kind, i, u, a_thr, thr_is_row);
             StepRes res;
             env_step_f(p, st, u, a_thr, obs, res, fl, sKf);
             ep_len = st.k; ep_ret = st.ep_ret;

@@ -18,6 +18,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "rl_rocket_b200.h"
 
 #ifndef RLR_REGS6
@@ -83,8 +85,28 @@ RLR_DEV float np_cosf_small(float x) {
     r = __fmaf_rn(r, x2, 1.0f);
     return r;
 }
-RLR_DEV float np_sinf(float x) { return fabsf(x) < 0.78539816f ? np_sinf_small(x) : (float)sin((double)x); }
-RLR_DEV float np_cosf(float x) { return fabsf(x) < 0.78539816f ? np_cosf_small(x) : (float)cos((double)x); }
+// Any argument up to numpy's Cody-Waite limit (cos 71476.0625, sin 117435.992): quadrant k = rint(x 2/pi) by the 1.5 * 2^23
+// magic-number add with a FUSED multiply-add, three-term f32 reduction, both polynomials' choice by the parity of k (k + 1 for
+// cosine), negation by bit 1.  Bit-identical to np.sin / np.cos on every float32 with |x| <= 64 (checked exhaustively on the
+// host, tests/test_oracle_golden.py, through the C restatement the tests use).  The environments never clip the action (rocket_env.py:969-981),
+// so gimbal angles beyond pi/4 (|action| > 2.25) are legal inputs.  Beyond the limit numpy calls libm: correctly rounded double.
+__device__ __noinline__ float np_sincosf_reduced(float x, bool want_cos) {
+    const float lim = want_cos ? 71476.0625f : 117435.992f;
+    if (!(fabsf(x) <= lim)) return want_cos ? (float)cos((double)x) : (float)sin((double)x);
+    const float magic = 0x1.8p23f;
+    const float k = __fsub_rn(__fmaf_rn(x, 0.636619772367581343075535053490057448f, magic), magic);
+    float r = __fmaf_rn(k, -0x1.921fb0p+00f, x);
+    r = __fmaf_rn(k, -0x1.5110b4p-22f, r);
+    r = __fmaf_rn(k, -0x1.846988p-48f, r);
+    int ik = (int)k;
+    if (want_cos) ik += 1;
+    float v = ((ik & 1) == 0) ? np_sinf_small(r) : np_cosf_small(r);
+    if ((ik & 2) == 2) v = __fsub_rn(0.0f, v);
+    return v;
+}
+// |x| < pi/4 (every action inside the Box): k = 0 and r = x, i.e. the polynomials themselves -- kept inline, the rest out of line
+RLR_DEV float np_sinf(float x) { return fabsf(x) < 0.78539816f ? np_sinf_small(x) : np_sincosf_reduced(x, false); }
+RLR_DEV float np_cosf(float x) { return fabsf(x) < 0.78539816f ? np_cosf_small(x) : np_sincosf_reduced(x, true); }
 
 // f32 ops whose rounding is part of the reference's dtype flow: never contracted.
 RLR_DEV float fmul(float a, float b) { return __fmul_rn(a, b); }
@@ -709,6 +731,13 @@ __device__ __noinline__ void event_path6(const double2* __restrict__ sKt, double
 RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&y)[14], int& natt, double2* __restrict__ sKt) {
     // sKt = (double2*)sK + tid; slot (stage, pair p) holds components 2p, 2p+1 -> 128-bit shared-memory accesses
     constexpr double rtol = 1e-3, atol = 1e-6;
+#if !RLR_EXACT
+    // Zero mass: dv/dt is infinite.  scipy then gets h0 = 0.01 d0 / inf = 0, clamps it to min_step, rejects the one attempt (its error
+    // norm is NaN) and gives up with status -1 (rk.py:111-176; pinned by the zero_mass cases of tests/golden/traj_*_landing.npz).
+    // The exact build walks through this with IEEE infinities; the Newton reciprocals of the fast build would turn the infinity into
+    // a NaN at once, so the outcome is stated directly.
+    if (y[13] == 0.0) { natt = 1; return -1; }
+#endif
 #define KS2(j, p) sKt[(j) * KROW + (p) * BS6]
 #define KS(j, cc) (((cc) & 1) ? KS2(j, (cc) >> 1).y : KS2(j, (cc) >> 1).x)
     double kk[10];
@@ -1084,6 +1113,7 @@ RLR_DEV int rk45_solve3(const Sys3::Ctx& c, double t0, double t_bound, double (&
     constexpr double rtol = 1e-3, atol = 1e-6;
     constexpr double INV_RS7 = 0.37796447300922722721;
     const double dom = (-0.0 - c.torque) * (1.0 / 6.04e6);
+    if (y[6] == 0.0) { natt = 1; return -1; }          // zero mass: see rk45_solve6
     double kx[7], kz[7];
     rhs3r(c, y[2], y[3], y[4], rcp_(y[6]), kx[0], kz[0]);
     natt = 0;
@@ -1257,6 +1287,10 @@ RLR_DEV void sample_ic_warp(const RlrParams& p, uint64_t seed, int64_t env, int3
     }
 }
 
+RLR_DEV void vtarg3(const RlrParams& p, const float (&s)[7], float v0, double (&vt)[4]);
+template <int NO>
+RLR_DEV void gaudet_obs3(const float (&s)[7], const double (&vt)[4], float (&obs)[NO]);
+
 // reset from an f32 IC: quaternion normalised in f32 (rocket_env.py:673), v0 = f32 norm of IC velocity
 template <class S>
 RLR_DEV void reset_from_ic(const RlrParams& p, float (&ic)[S::N], double (&y)[S::N], float& v0, float (&obs)[S::N]) {
@@ -1276,6 +1310,13 @@ RLR_DEV void reset_from_ic(const RlrParams& p, float (&ic)[S::N], double (&y)[S:
 #else
         obs[i] = (float)((double)ic[i] * p.inv_normalizer[i]);
 #endif
+    }
+    if constexpr (S::N == 7) {
+        if (p.obs_mode == RLR_OBS_GAUDET) {      // ObservationWrapper.reset -> observation(): vtarg of the initial condition
+            double vt[4];
+            vtarg3(p, (const float(&)[7])ic, v0, vt);
+            gaudet_obs3((const float(&)[7])ic, vt, obs);
+        }
     }
 }
 
@@ -1366,8 +1407,8 @@ RLR_DEV void reward6(const RlrParams& p, const float (&s)[14], const float* u, f
     o.done = (status != 0) || viol;
 }
 
-// Rocket._compute_reward / _compute_vtarg / _check_landing / _check_bounds (rocket_env.py:177-247, 431-476)
-RLR_DEV void reward3(const RlrParams& p, const float (&s)[7], const float* u, float a_thr, float v0, int status, StepRes& o) {
+// Rocket._compute_vtarg (rocket_env.py:219-247) on the f32 state: vt = [v_targ_x, v_targ_z, 0, t_go]
+RLR_DEV void vtarg3(const RlrParams& p, const float (&s)[7], float v0, double (&vt)[4]) {
     double rh0, rh1, vh1, tau;
     if ((double)s[1] > p.waypoint) {
         rh0 = (double)s[0]; rh1 = (double)s[1] - p.waypoint; vh1 = (double)s[4] - (-2.0); tau = 20.0;
@@ -1382,7 +1423,7 @@ RLR_DEV void reward3(const RlrParams& p, const float (&s)[7], const float* u, fl
     const double den = py_max(1e-3, nr);
     const double fac = 1 - exp(-t_go / tau);
     const double mv0 = (double)(-v0);
-    const double vt0 = (mv0 * (rh0 / den)) * fac, vt1 = (mv0 * (rh1 / den)) * fac;
+    vt[0] = (mv0 * (rh0 / den)) * fac; vt[1] = (mv0 * (rh1 / den)) * fac;
 #else
     const double nr = sqrt_(rh0 * rh0 + rh1 * rh1);
     const double nv = sqrt_(vh0 * vh0 + vh1 * vh1);
@@ -1391,10 +1432,24 @@ RLR_DEV void reward3(const RlrParams& p, const float (&s)[7], const float* u, fl
     const double fac = 1 - exp(-t_go * rcp_(tau));
     const double mv0 = (double)(-v0);
     const double iden = rcp_(den);
-    const double vt0 = (mv0 * (rh0 * iden)) * fac, vt1 = (mv0 * (rh1 * iden)) * fac;
+    vt[0] = (mv0 * (rh0 * iden)) * fac; vt[1] = (mv0 * (rh1 * iden)) * fac;
 #endif
-    const double d0 = (double)s[3] - vt0, d1 = (double)s[4] - vt1;
-    o.vt[0] = vt0; o.vt[1] = vt1; o.vt[2] = 0.0; o.vt[3] = t_go;
+    vt[2] = 0.0; vt[3] = t_go;
+}
+
+// GaudetStateObs (wrappers.py:51-66), corrected: np.float32([vx - vtarg_x, vz - vtarg_z, t_go, z]) of the physical f32 state
+template <int NO>
+RLR_DEV void gaudet_obs3(const float (&s)[7], const double (&vt)[4], float (&obs)[NO]) {
+    obs[0] = (float)((double)s[3] - vt[0]);
+    obs[1] = (float)((double)s[4] - vt[1]);
+    obs[2] = (float)vt[3];
+    obs[3] = s[1];
+}
+
+// Rocket._compute_reward / _compute_vtarg / _check_landing / _check_bounds (rocket_env.py:177-247, 431-476)
+RLR_DEV void reward3(const RlrParams& p, const float (&s)[7], const float* u, float a_thr, bool thr_is_row, float v0, int status, StepRes& o) {
+    vtarg3(p, s, v0, o.vt);
+    const double d0 = (double)s[3] - o.vt[0], d1 = (double)s[4] - o.vt[1];
     const float zeta = fadd(s[2], -1.5707963267948966f);
     const float az = fabsf(zeta);
     const float rn = f32_norm2(s[0], s[1]), vn = f32_norm2(s[3], s[4]);
@@ -1415,11 +1470,17 @@ RLR_DEV void reward3(const RlrParams& p, const float (&s)[7], const float* u, fl
     o.terms[5] = p.kappa * (double)landed;
     double r = ((((o.terms[0] + o.terms[1]) + o.terms[2]) + o.terms[3]) + o.terms[4]) + o.terms[5];
     if (viol) r += -50.0;
-    if (p.reward_mode == 1) {               // python float + np.float32 -> f32 arithmetic
-        const float tp = fmul((float)(-p.xi), fadd(a_thr, 1.0f));
-        const float rr = fadd((float)(o.terms[3] + o.terms[5]), tp);
-        r = (double)rr;
-        o.terms[1] = (double)tp;
+    if (p.reward_mode == 1) {
+        if (thr_is_row) {                   // DiscreteActions3DOF(RewardAnnealing(env)): python float * np.int64 -> float64
+            const double tp = (-p.xi) * ((double)a_thr + 1.0);
+            r = (o.terms[3] + o.terms[5]) + tp;
+            o.terms[1] = tp;
+        } else {                            // python float + np.float32 -> f32 arithmetic
+            const float tp = fmul((float)(-p.xi), fadd(a_thr, 1.0f));
+            const float rr = fadd((float)(o.terms[3] + o.terms[5]), tp);
+            r = (double)rr;
+            o.terms[1] = (double)tp;
+        }
     }
     o.reward = r; o.viol = viol; o.landed = landed; o.status = status;
     o.done = (status != 0) || viol;
@@ -1435,9 +1496,12 @@ struct EnvState {
 };
 
 // action -> physical f32 u (+ the normalised throttle for RewardAnnealing)
+// a_thr: normalised throttle RewardAnnealing sees; thr_is_row: it is a DiscreteActions3DOF table row (an int64 in the reference, so
+// the annealed penalty is evaluated in float64, wrappers.py:34, :80)
 template <class S>
-RLR_DEV void map_action(const RlrParams& p, const void* actions, int action_kind, int64_t i, float (&u)[3], float& a_thr) {
+RLR_DEV void map_action(const RlrParams& p, const void* actions, int action_kind, int64_t i, float (&u)[3], float& a_thr, bool& thr_is_row) {
     a_thr = 0.0f;
+    thr_is_row = false;
     if constexpr (S::N == 14) {
         const float* a = (const float*)actions + i * 3;
         const float a0 = a[0], a1 = a[1], a2 = a[2];
@@ -1453,6 +1517,8 @@ RLR_DEV void map_action(const RlrParams& p, const void* actions, int action_kind
             long long idx = ((const long long*)actions)[i];
             idx = idx < 0 ? 0 : (idx >= p.n_discrete ? p.n_discrete - 1 : idx);
             u[0] = p.discrete_table[2 * idx]; u[1] = p.discrete_table[2 * idx + 1]; u[2] = 0.0f;
+            a_thr = p.discrete_thr[idx];
+            thr_is_row = true;
             return;
         }
         if (p.dof == 1) { a0 = 0.0f; a1 = ((const float*)actions)[i]; }
@@ -1471,8 +1537,8 @@ struct StepFlags { int done, trunc, viol, landed, status, natt; };
 // Integrate one env step, compute reward/obs/flags.  `st` is updated to the post-step state
 // (NOT reset).  obs = observation of the post-step state.
 template <class S>
-RLR_DEV void env_step(const RlrParams& p, EnvState<S>& st, const float (&u)[3], float a_thr, float (&obs)[S::N], StepRes& res, StepFlags& fl,
-                      double* sK) {
+RLR_DEV void env_step(const RlrParams& p, EnvState<S>& st, const float (&u)[3], float a_thr, bool thr_is_row, float (&obs)[S::N], StepRes& res,
+                      StepFlags& fl, double* sK) {
     typename S::Ctx c;
     S::make_ctx(c, u);
     const double t = (double)((long long)st.k * (long long)p.dt_ms) / 1000.0;   // round(t + dt, 3)  (simulator.py:245)
@@ -1521,7 +1587,8 @@ RLR_DEV void env_step(const RlrParams& p, EnvState<S>& st, const float (&u)[3], 
 #endif
 #pragma unroll
         for (int i = 0; i < S::N; ++i) { s[i] = (float)st.y[i]; obs[i] = (float)((double)s[i] / p.normalizer[i]); }   // rocket_env.py:155,:175,:209-210
-        reward3(p, (const float(&)[7])s, u, a_thr, st.v0, status, res);
+        reward3(p, (const float(&)[7])s, u, a_thr, thr_is_row, st.v0, status, res);
+        if (p.obs_mode == RLR_OBS_GAUDET) gaudet_obs3(s, res.vt, obs);
     }
     st.k += 1;
     st.ep_ret += res.reward;
@@ -1550,7 +1617,10 @@ RLR_DEV void store_state(const RlrState& gs, int64_t n, int64_t i, const EnvStat
 template <class S>
 RLR_DEV void write_obs(const RlrParams& p, float* dst, int64_t i, const float (&obs)[S::N]) {
     if (p.dof == 1) { dst[i * 2] = obs[1]; dst[i * 2 + 1] = obs[4]; }
-    else {
+    else if (S::N == 7 && p.obs_mode == RLR_OBS_GAUDET) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dst[i * 4 + c] = obs[c];
+    } else {
 #pragma unroll
         for (int c = 0; c < S::N; ++c) dst[i * S::N + c] = obs[c];
     }
@@ -1636,12 +1706,13 @@ RLR_DEV void finish_and_reset(const RlrParams& p, EnvState<S>& st, const float* 
 
 template <class S>
 __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrParams p, RlrState gs, const void* actions, int action_kind,
-                                                   const float* ic_inject, RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed,
-                                                   bool stage_obs) {
+                                                   const float* ic_inject, RlrStepOut out, int64_t n, int64_t i_begin, int64_t i_end,
+                                                   int64_t env_offset, uint64_t seed, bool stage_obs) {
+    // environments [i_begin, i_end) of a batch of n (n is the structure-of-arrays stride; rlr_step passes 0, n)
     extern __shared__ double sK[];
     pdl_launch_dependents();
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = i < n;
+    const int64_t i = i_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = i < i_end;
     StepFlags fl = {0, 0, 0, 0, 0, 0};
     int ep_len = 0;
     double ep_ret = 0.0;
@@ -1653,10 +1724,11 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
     if (active) {
         load_state<S>(gs, n, i, st);
         float u[3], a_thr;
-        map_action<S>(p, actions, action_kind, i, u, a_thr);
+        bool thr_is_row;
+        map_action<S>(p, actions, action_kind, i, u, a_thr, thr_is_row);
         StepRes res;
         RLR_PHASE(0);                   // 0: state / action loads
-        env_step<S>(p, st, u, a_thr, obs, res, fl, sK);
+        env_step<S>(p, st, u, a_thr, thr_is_row, obs, res, fl, sK);
         RLR_PHASE(4);                   // 4: normalise, obs, reward
         ep_len = st.k; ep_ret = st.ep_ret;
         if (out.reward) out.reward[i] = (float)res.reward;
@@ -1733,7 +1805,7 @@ __global__ void RLR_KERNEL_BOUNDS(S) rollout_kernel(const __grid_constant__ RlrP
     st.episode = 0;
     if (active) load_state<S>(gs, n, i, st);
     const int na = (p.dof == 1) ? 1 : S::NA;
-    const int no = (p.dof == 1) ? 2 : S::NOBS;
+    const int no = (p.dof == 1) ? 2 : ((S::N == 7 && p.obs_mode == RLR_OBS_GAUDET) ? 4 : S::NOBS);
     float obs[S::N];
 #pragma unroll 1
     for (int t = 0; t < T; ++t) {
@@ -1744,9 +1816,10 @@ __global__ void RLR_KERNEL_BOUNDS(S) rollout_kernel(const __grid_constant__ RlrP
             const void* a_t = (action_kind == RLR_ACT_DISCRETE) ? (const void*)((const long long*)actions + (int64_t)t * n)
                                                                 : (const void*)((const float*)actions + (int64_t)t * n * na);
             float u[3], a_thr;
-            map_action<S>(p, a_t, action_kind, i, u, a_thr);
+            bool thr_is_row;
+            map_action<S>(p, a_t, action_kind, i, u, a_thr, thr_is_row);
             StepRes res;
-            env_step<S>(p, st, u, a_thr, obs, res, fl, sK);
+            env_step<S>(p, st, u, a_thr, thr_is_row, obs, res, fl, sK);
             ep_len = st.k; ep_ret = st.ep_ret;
             if (reward_buf) reward_buf[(int64_t)t * n + i] = (float)res.reward;
             if (done_buf) done_buf[(int64_t)t * n + i] = (uint8_t)fl.done;
@@ -1768,13 +1841,6 @@ __global__ void RLR_KERNEL_BOUNDS(S) rollout_kernel(const __grid_constant__ RlrP
     }
 }
 
-#ifndef RLR_PAIR6
-#define RLR_PAIR6 0                 // 1: warp-specialised two-threads-per-environment 6DOF kernels (rocket_pair6.cuh) -- measured slower
-#endif
-#if RLR_PAIR6
-#include "experimental/rocket_pair6.cuh"
-#endif
-
 #if !RLR_EXACT
 #include "rocket_f32.cuh"           // RLR_F32 precision of the 6DOF path (fast build only)
 #endif
@@ -1785,24 +1851,37 @@ __global__ void RLR_KERNEL_BOUNDS(S) rollout_kernel(const __grid_constant__ RlrP
 // reduced (by padding the dynamic shared-memory request) to the value that maximises  utilisation * sqrt(resident blocks)
 // -- e.g. 65 536 envs on 148 SMs: 7 blocks/SM -> 1024 blocks on 1036 slots, one wave.
 struct Geometry { int block; size_t smem; int blocks_per_sm; };
-struct GeometryEntry { const void* kern; int64_t n; Geometry g; };
+struct GeometryEntry { const void* kern; int64_t n; int dev; Geometry g; };
+struct DeviceInfo { int sm_count, smem_per_sm; };
+
+// Launch-geometry state is per DEVICE (cudaFuncSetAttribute applies to the current device only) and guarded by a mutex: ctypes
+// releases the GIL around every call, so two host threads (or two batches on two GPUs of one process) may be in here at once.
+inline std::mutex& geometry_mutex() { static std::mutex m; return m; }
+
+inline DeviceInfo device_info(int dev) {           // call with geometry_mutex held
+    static DeviceInfo info[64] = {};
+    DeviceInfo& d = info[dev & 63];
+    if (d.sm_count == 0) {
+        cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&d.smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        if (d.sm_count <= 0) d.sm_count = 148;
+        if (d.smem_per_sm <= 0) d.smem_per_sm = 233472;
+    }
+    return d;
+}
 
 template <typename Kern>
 Geometry pick_geometry(Kern kern, int64_t n, int block, size_t smem_min) {
-    static int sm_count = 0, smem_per_sm = 0;
-    static GeometryEntry cache[8] = {};
+    static GeometryEntry cache[16] = {};
     static int cache_next = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
     const void* key = (const void*)kern;
-    for (int e = 0; e < 8; ++e)
-        if (cache[e].kern == key && cache[e].n == n) return cache[e].g;
-    if (sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-        cudaDeviceGetAttribute(&smem_per_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-        if (sm_count <= 0) sm_count = 148;
-        if (smem_per_sm <= 0) smem_per_sm = 233472;
-    }
+    std::lock_guard<std::mutex> lock(geometry_mutex());
+    for (int e = 0; e < 16; ++e)
+        if (cache[e].kern == key && cache[e].n == n && cache[e].dev == dev) return cache[e].g;
+    const DeviceInfo di = device_info(dev);
+    const int sm_count = di.sm_count, smem_per_sm = di.smem_per_sm;
     Geometry best = {block, smem_min, 1};
     int nb_max = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb_max, kern, block, smem_min) != cudaSuccess || nb_max <= 0) nb_max = 1;
@@ -1821,11 +1900,13 @@ Geometry pick_geometry(Kern kern, int64_t n, int block, size_t smem_min) {
             if (padded > 227 * 1024) padded = 227 * 1024;
             if (padded > smem_min) best.smem = padded;
         }
-        if (best.smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)best.smem);
+        // the opt-in limit is a per-device function attribute: raise it to the cap once per (kernel, device) so that every later
+        // padded request on this device is legal whatever batch size asked first
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     }
     cudaGetLastError();
-    cache[cache_next] = {key, n, best};
-    cache_next = (cache_next + 1) % 8;
+    cache[cache_next] = {key, n, dev, best};
+    cache_next = (cache_next + 1) % 16;
     return best;
 }
 
@@ -1847,40 +1928,37 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int block, size_
     return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
 }
 
-// true when `ptr` is (mapped, pinned) host memory; the answer for the last pointer asked about is cached (one driver query per buffer)
+// true when `ptr` is (mapped, pinned) host memory.  A small per-thread cache keeps the driver query off the hot path even when a
+// caller alternates between device and host destinations (step_tensor / step_host on one batch).
 inline bool is_host_pointer(const void* ptr) {
-    static const void* last_ptr = nullptr;
-    static bool last_answer = false;
-    if (ptr == last_ptr) return last_answer;
+    struct Entry { const void* ptr; bool host; };
+    thread_local Entry cache[4] = {};
+    thread_local int next = 0;
+    for (int e = 0; e < 4; ++e)
+        if (cache[e].ptr == ptr && ptr != nullptr) return cache[e].host;
     cudaPointerAttributes attr;
     bool host = false;
     if (cudaPointerGetAttributes(&attr, ptr) == cudaSuccess) host = (attr.type == cudaMemoryTypeHost);
     cudaGetLastError();
-    last_ptr = ptr; last_answer = host;
+    cache[next] = {ptr, host};
+    next = (next + 1) & 3;
     return host;
 }
 
 int launch_step(const RlrParams* p, RlrState st, const void* actions, int action_kind, const float* ic_inject, RlrStepOut out, int64_t n,
-                int64_t env_offset, uint64_t seed, cudaStream_t stream) {
+                int64_t begin, int64_t count, int64_t env_offset, uint64_t seed, cudaStream_t stream) {
+    const int64_t end = begin + count;
     if (p->dof == 6) {
-#if RLR_PAIR6
-        static bool carveout_set = false;
-        if (!carveout_set) {
-            cudaFuncSetAttribute(pair6::pair_step_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            carveout_set = true;
-        }
-        pair6::pair_step_kernel<<<grid_for(n, pair6::ENVS), pair6::THREADS, pair6::SMEM_BYTES, stream>>>(
-            *p, st, (const float*)actions, action_kind, ic_inject, out, n, env_offset, seed);
-        return (int)cudaGetLastError();
-#endif
-        const Geometry g = pick_geometry(step_kernel<Sys6>, n, BS6, SMEM6_BYTES);
-        launch_pdl(step_kernel<Sys6>, grid_for(n, g.block), g.block, g.smem, stream, *p, st, actions, action_kind, ic_inject, out, n, env_offset,
-                   seed, is_host_pointer(out.obs));
+        const Geometry g = pick_geometry(step_kernel<Sys6>, count, BS6, SMEM6_BYTES);
+        launch_pdl(step_kernel<Sys6>, grid_for(count, g.block), g.block, g.smem, stream, *p, st, actions, action_kind, ic_inject, out, n, begin,
+                   end, env_offset, seed, is_host_pointer(out.obs));
     } else {
-        if (n > 148 * 3 * 128)
-            launch_pdl(step_kernel<Sys3Dense>, grid_for(n, 128), 128, 0, stream, *p, st, actions, action_kind, ic_inject, out, n, env_offset, seed, false);
+        if (count > 148 * 3 * 128)
+            launch_pdl(step_kernel<Sys3Dense>, grid_for(count, 128), 128, 0, stream, *p, st, actions, action_kind, ic_inject, out, n, begin, end,
+                       env_offset, seed, false);
         else
-            launch_pdl(step_kernel<Sys3>, grid_for(n, 128), 128, 0, stream, *p, st, actions, action_kind, ic_inject, out, n, env_offset, seed, false);
+            launch_pdl(step_kernel<Sys3>, grid_for(count, 128), 128, 0, stream, *p, st, actions, action_kind, ic_inject, out, n, begin, end,
+                       env_offset, seed, false);
     }
     return (int)cudaGetLastError();
 }
@@ -1897,16 +1975,6 @@ int launch_rollout(const RlrParams* p, RlrState st, const void* actions, int act
                    uint8_t* done_buf, uint8_t* trunc_buf, float* last_obs, unsigned long long* stats, int64_t n, int64_t env_offset,
                    uint64_t seed, cudaStream_t stream) {
     if (p->dof == 6) {
-#if RLR_PAIR6
-        static bool carveout_set = false;
-        if (!carveout_set) {
-            cudaFuncSetAttribute(pair6::pair_rollout_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            carveout_set = true;
-        }
-        pair6::pair_rollout_kernel<<<grid_for(n, pair6::ENVS), pair6::THREADS, pair6::SMEM_BYTES, stream>>>(
-            *p, st, (const float*)actions, action_kind, T, obs_buf, reward_buf, done_buf, trunc_buf, last_obs, stats, n, env_offset, seed);
-        return (int)cudaGetLastError();
-#endif
         const Geometry g = pick_geometry(rollout_kernel<Sys6>, n, BS6, SMEM6_BYTES);
         rollout_kernel<Sys6><<<grid_for(n, g.block), g.block, g.smem, stream>>>(*p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf,
                                                                               trunc_buf, last_obs, stats, n, env_offset, seed);
@@ -1924,9 +1992,9 @@ int launch_rollout(const RlrParams* p, RlrState st, const void* actions, int act
 #if !RLR_EXACT
 // RLR_F32 precision (6DOF only): 128-thread blocks, 27 KB of dynamic shared memory for the binary32 stage matrix
 int launch_step_f32(const RlrParams* p, RlrState st, const void* actions, int action_kind, const float* ic_inject, RlrStepOut out, int64_t n,
-                    int64_t env_offset, uint64_t seed, cudaStream_t stream) {
-    launch_pdl(f32::step_kernel_f32, grid_for(n, f32::BSF), f32::BSF, f32::SMEMF_BYTES, stream, *p, st, (const float*)actions, action_kind, ic_inject,
-               out, n, env_offset, seed, is_host_pointer(out.obs));
+                    int64_t begin, int64_t count, int64_t env_offset, uint64_t seed, cudaStream_t stream) {
+    launch_pdl(f32::step_kernel_f32, grid_for(count, f32::BSF), f32::BSF, f32::SMEMF_BYTES, stream, *p, st, (const float*)actions, action_kind,
+               ic_inject, out, n, begin, begin + count, env_offset, seed, is_host_pointer(out.obs));
     return (int)cudaGetLastError();
 }
 int launch_reset_f32(const RlrParams* p, RlrState st, const uint8_t* mask, const float* ic_inject, float* obs, int64_t n, int64_t env_offset,

@@ -58,6 +58,7 @@ class RocketBatch:
         self.reward_terms = torch.zeros((6, n), dtype=torch.float64, device=dev) if self.debug else None
         self.vtarg = torch.zeros((4, n), dtype=torch.float64, device=dev) if self.debug else None
         self.launches = 0
+        self._started = False        # True once reset() has drawn initial conditions: later explicit resets move to the NEXT episode key
         # the buffers above are persistent, so the pointer structs handed to the C ABI are built once
         self._st = N.RlrState(_ptr(self.y), _ptr(self.k), _ptr(self.episode), _ptr(self.v0), _ptr(self.ep_ret))
         self._ot = N.RlrStepOut(_ptr(self.obs), _ptr(self.reward), _ptr(self.reward64), _ptr(self.done), _ptr(self.truncated),
@@ -103,14 +104,31 @@ class RocketBatch:
         return actions, kind
 
     # -- API ----------------------------------------------------------------------------------
+    def reseed(self, seed):
+        """gym's `seed()`: re-key the reset RNG and restart the episode numbering, so that seed(s) + reset() reproduces."""
+        self.seed = int(seed)
+        self.episode.zero_()
+        self._started = False
+
     def reset(self, mask=None, ic=None):
-        """(Re)start environments; returns the obs tensor [n, nobs] (device).  `ic`: optional f32 [n, ndim] initial conditions."""
+        """(Re)start environments; returns the obs tensor [n, nobs] (device).  `ic`: optional f32 [n, ndim] initial conditions.
+
+        Initial conditions are Philox draws keyed by (seed, global env index, episode index).  The first reset after construction
+        (or reseed) uses each environment's current episode index; every later explicit reset first advances the index of the
+        environments it restarts, so that -- like `init_space.sample()` in the reference (rocket_env.py:142, :672) -- it draws
+        fresh initial conditions instead of replaying the running episode's."""
         with torch.cuda.device(self.device):
             if ic is not None:
                 ic = torch.as_tensor(ic, dtype=torch.float32, device=self.device).contiguous()
                 assert tuple(ic.shape) == (self.n, self.spec.ndim)
             if mask is not None:
                 mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+            if self._started:
+                if mask is None:
+                    self.episode += 1
+                else:
+                    self.episode += (mask != 0).to(torch.int32)
+            self._started = True
             N.check(self.lib.rlr_reset(self._params_ref, self.precision, self._state(), _ptr(mask), _ptr(ic), _ptr(self.obs),
                                        self.n, self.env_offset, self.seed, self._stream()))
             self.launches += 1
@@ -121,12 +139,15 @@ class RocketBatch:
         (views of persistent buffers, overwritten by the next call)."""
         if (actions.dtype is torch.float32 and tuple(actions.shape) == self._act_shape and actions.is_contiguous()
                 and actions.device == self.device and ic_inject is None):
-            # hot path: no per-call allocation, one ctypes call
-            if torch.cuda.current_device() != self._dev_index:
+            # hot path: no per-call allocation, one ctypes call (the caller's current device is restored when it was another GPU)
+            prev = torch.cuda.current_device()
+            if prev != self._dev_index:
                 torch.cuda.set_device(self._dev_index)
             rc = self._step_fn(self._params_ref, self.precision, self.math_mode, self._st, actions.data_ptr(),
                                N.ACT_PHYSICAL if physical else N.ACT_NORMALIZED, None, self._ot, self.n, self.env_offset, self.seed,
                                torch.cuda.current_stream(self._dev_index).cuda_stream)
+            if prev != self._dev_index:
+                torch.cuda.set_device(prev)
             if rc:
                 N.check(rc)
             self.launches += 1
@@ -144,16 +165,26 @@ class RocketBatch:
 
     def step_out_struct(self, obs, reward, done):
         """An RlrStepOut whose obs / reward / done point at caller-owned buffers (e.g. mapped pinned HOST memory: the kernel then
-        writes the step's results straight across PCIe, see RocketVecEnv.step_host); every other output stays on the device."""
+        writes the step's results straight across PCIe, see RocketVecEnv.step_host); every other output stays on the device.
+        NB: a step through this struct does not refresh the batch's own `obs` / `reward` / `reward64` / `done` tensors."""
         return N.RlrStepOut(_ptr(obs), _ptr(reward), None, _ptr(done), _ptr(self.truncated), _ptr(self.terminal_obs), _ptr(self.fin_ret),
                             _ptr(self.fin_len), _ptr(self.flags), None, None, None, None, _ptr(self.stats))
 
-    def step_raw(self, actions_ptr, out_struct):
-        """One step with a raw f32 [n, nact] action pointer (device, or mapped pinned host memory) and a custom output struct."""
-        if torch.cuda.current_device() != self._dev_index:
+    def step_raw(self, actions_ptr, out_struct, stream=None, begin=0, count=None, action_kind=N.ACT_NORMALIZED):
+        """One step with a raw action pointer (device, or mapped pinned host memory) and a custom output struct, optionally for the
+        sub-range [begin, begin + count) of the environments only and on an explicit CUDA stream (sub-batch pipelining: several
+        ranges on several streams, see RocketVecEnv.step_host_async)."""
+        prev = torch.cuda.current_device()
+        if prev != self._dev_index:
             torch.cuda.set_device(self._dev_index)
-        rc = self._step_fn(self._params_ref, self.precision, self.math_mode, self._st, actions_ptr, N.ACT_NORMALIZED, None, out_struct,
-                           self.n, self.env_offset, self.seed, torch.cuda.current_stream(self._dev_index).cuda_stream)
+        if stream is None:
+            stream = torch.cuda.current_stream(self._dev_index).cuda_stream
+        if count is None:
+            count = self.n - begin
+        rc = self.lib.rlr_step_range(self._params_ref, self.precision, self.math_mode, self._st, actions_ptr, action_kind, None,
+                                     out_struct, self.n, begin, count, self.env_offset, self.seed, stream)
+        if prev != self._dev_index:
+            torch.cuda.set_device(prev)
         if rc:
             N.check(rc)
         self.launches += 1

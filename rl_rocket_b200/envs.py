@@ -50,8 +50,7 @@ class _SingleEnv(spaces.GymEnv):
     # ---- gym API
     def seed(self, seed=42):
         """Keys the device-side Philox IC sampler (the reference seeds gym's RandomState here, rocket_env.py:478-480)."""
-        self._batch.seed = int(seed)
-        self._batch.episode.zero_()
+        self._batch.reseed(seed)
         self.init_space.seed(seed)
         return [seed]
 
@@ -62,7 +61,6 @@ class _SingleEnv(spaces.GymEnv):
         self.initial_condition = y.astype(np.float32)
         self._set_state(self.initial_condition)
         self.SIM = _History(self.initial_condition, self._spec.nact if self._dof != 1 else 2)
-        self._batch.episode += 1            # the next reset() draws a fresh IC
         return self._format_obs(obs[0].cpu().numpy(), self.initial_condition)
 
     def step(self, normalized_action):

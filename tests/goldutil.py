@@ -20,25 +20,13 @@ def load(name):
 
 
 def cfg6():
-    pi = np.pi
-    return {
-        "timestep": 0.1, "seed": 42,
-        "IC": [500, 100, 100, -50, 0, 0, 1, 0, 0, 0, 0, 0, 0, 45e3],
-        "ICRange": [50, 10, 10, 10, 10, 10, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 0.1, 1e3],
-        "reward_coeff": {"alfa": -0.01, "beta": -1e-7, "delta": -5, "eta": 0.05, "gamma": -10, "kappa": 10, "xi": 0.004},
-        "trajectory_limits": {"attitude_limit": [1.5, 1.5, 2 * pi]},
-        "landing_params": {"waypoint": 50, "landing_radius": 30, "maximum_velocity": 10,
-                           "landing_attitude_limit": [10 / 180 * pi, 10 / 180 * pi, 2 * pi], "omega_lim": [0.2, 0.2, 0.2]},
-    }
+    from rl_rocket_b200.config import env_config_6dof
+    return env_config_6dof()
 
 
 def cfg3():
-    pi = np.pi
-    return {
-        "IC": [-1600, 2000, pi * 3 / 4, 180, -90, 0, 50e3], "ICRange": [5, 50, 0, 0, 0, 0, 1e3], "timestep": 0.05, "seed": 42,
-        "reward_coeff": {"alfa": -0.01, "beta": 0, "delta": -5, "eta": 0.2, "gamma": -10, "kappa": 10, "xi": 0.004,
-                         "waypoint": 30, "landing_radius": 30},
-    }
+    from rl_rocket_b200.config import env_config_3dof
+    return env_config_3dof()
 
 
 def cfg3_default():
@@ -48,8 +36,31 @@ def cfg3_default():
 
 
 def cfg1():
-    return dict(IC=[0, 2000, np.pi / 2, 0, -90, 0, 50e3], ICRange=[0, 50, 0, 0, 0, 0, 1e3], timestep=0.05, seed=42,
-                reward_coeff=cfg3()["reward_coeff"])
+    from rl_rocket_b200.config import env_config_1dof
+    return env_config_1dof()
+
+
+def cfg6_landing_attitude():
+    """env_config with a landing attitude limit that CAN fail (the configured [10 deg, 10 deg, 2 pi] cannot: |angle| <= pi)."""
+    c = cfg6()
+    c["landing_params"] = {"waypoint": 50, "landing_radius": 30, "maximum_velocity": 10, "landing_attitude_limit": [0.1, 0.1, 0.1],
+                           "omega_lim": [0.2, 0.2, 0.2]}
+    return c
+
+
+def cfg6_landing_random():
+    c = cfg6()
+    c["IC"] = [4, 0, 0, -6, 0, 0, 1, 0, 0, 0, 0, 0, 0, 45e3]
+    c["ICRange"] = [4, 70, 70, 12, 4, 4, 0.2, 0.2, 0.2, 0.2, 0.8, 0.8, 0.8, 1e3]
+    return c
+
+
+def _zero_range(cfgf):
+    def f():
+        c = cfgf()
+        c["ICRange"] = [0] * len(c["IC"])
+        return c
+    return f
 
 
 DISCRETE_TABLE = [[0, -1], [-1, +1], [0, +1], [+1, +1]]
@@ -72,7 +83,23 @@ TRAJ = {
     "traj_3dof_discrete.npz": (3, cfg3, 3000, 0, "discrete"),
     "traj_3dof_annealing.npz": (3, cfg3, 3000, 1, "norm"),
     "traj_1dof.npz": (1, cfg1, 3000, 0, "norm"),
+    # round 2: the branches round 1 left unpinned -- touchdowns with rew_goal != 0 (np.any vs np.all, each landing limit from both
+    # sides, adjacent float32 ICs around the speed / radius thresholds), integrator failure (zero mass: solve_ivp status -1),
+    # actions outside the Box (numpy's float32 sin / cos range reduction), DiscreteActions3DOF(RewardAnnealing(...)).
+    # Files that carry an "ics" array restart every episode of env i from ics[i] (injected initial conditions).
+    "traj_6dof_landing.npz": (6, _zero_range(cfg6), 800, 0, "norm"),
+    "traj_6dof_landing_attitude.npz": (6, _zero_range(cfg6_landing_attitude), 800, 0, "norm"),
+    "traj_6dof_landing_random.npz": (6, cfg6_landing_random, 800, 0, "norm"),
+    "traj_3dof_landing.npz": (3, _zero_range(cfg3), 3000, 0, "norm"),
+    "traj_6dof_unclipped.npz": (6, cfg6, 800, 0, "norm"),
+    "traj_3dof_unclipped.npz": (3, cfg3, 3000, 0, "norm"),
+    "traj_3dof_discrete_annealing.npz": (3, cfg3, 3000, 1, "discrete"),
 }
+# observation mode per file (default: the normalised state): GaudetStateObs (wrappers.py:51-66) with its defects fixed, generated
+# by oracle/make_golden.py::gaudet_fixed over the live reference environment
+OBS_MODE = {"traj_3dof_gaudet.npz": 1, "traj_3dof_default_gaudet.npz": 1}
+TRAJ["traj_3dof_gaudet.npz"] = (3, cfg3, 3000, 0, "norm")
+TRAJ["traj_3dof_default_gaudet.npz"] = (3, cfg3_default, 2000, 0, "norm")
 
 
 def compare_step(tag, t, normalizer, g, got_y, got_obs, got_reward, got_done, got_trunc, got_natt=None, state_tol=STATE_TOL,
@@ -86,6 +113,7 @@ def compare_step(tag, t, normalizer, g, got_y, got_obs, got_reward, got_done, go
     assert np.nanmax(dev) <= state_tol, f"{tag} step {t}: state deviates {np.nanmax(dev):.3e}"
     rdev = np.abs(np.asarray(got_reward) - g["reward"]) / np.maximum(1.0, np.abs(g["reward"]))
     assert rdev.max() <= reward_tol, f"{tag} step {t}: reward deviates {rdev.max():.3e}"
-    odev = np.abs(np.asarray(got_obs, np.float64) - g["obs"].astype(np.float64))
+    gobs = g["obs"].astype(np.float64)
+    odev = np.abs(np.asarray(got_obs, np.float64) - gobs) / np.maximum(1.0, np.abs(gobs))     # (1 f32 ulp, also for un-normalised rows)
     assert odev.max() <= obs_tol, f"{tag} step {t}: obs deviates {odev.max():.3e}"
     return float(np.nanmax(dev)), float(rdev.max())

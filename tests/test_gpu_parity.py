@@ -18,7 +18,7 @@ def _engine():
 def _spec(name, **over):
     EnvSpec, _ = _engine()
     dof, cfgf, tl, mode, akind = G.TRAJ[name]
-    kw = dict(max_episode_steps=tl, reward_mode=mode, **cfgf())
+    kw = dict(max_episode_steps=tl, reward_mode=mode, obs_mode=G.OBS_MODE.get(name, 0), **cfgf())
     if akind == "discrete":
         kw["discrete_table"] = G.DISCRETE_TABLE
     kw.update(over)

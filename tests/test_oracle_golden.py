@@ -89,19 +89,20 @@ def test_kat4_vtarg_grid():
 def test_trajectories_with_autoreset(name):
     dof, cfgf, tl, mode, akind = G.TRAJ[name]
     g = G.load(name)
-    p = O.make_params(dof, max_episode_steps=tl, reward_mode=mode, **cfgf())
+    p = O.make_params(dof, max_episode_steps=tl, reward_mode=mode, obs_mode=G.OBS_MODE.get(name, 0), **cfgf())
     norm = np.array(p.normalizer[:O.ndim(p)])
     T, N = g["done"].shape
     vec = O.VecOracle(p, N, seed=int(g["seed"]))
-    obs0 = vec.reset()                      # Philox ICs must reproduce the ICs stored in the golden file
+    ics = g["ics"] if "ics" in g.files else None     # crafted cases: every episode of env i restarts from ics[i]
+    obs0 = vec.reset(ics)                   # (otherwise) Philox ICs must reproduce the ICs stored in the golden file
     assert np.abs(obs0.astype(float) - g["obs0"]).max() <= G.OBS_TOL
     worst = 0.0
     for t in range(T):
         a = g["actions"][t]
         if akind == "discrete":
-            out = vec.step(G.discrete_to_physical(a), action_kind=1)
+            out = vec.step(np.asarray(G.DISCRETE_TABLE, np.float32)[a], action_kind=2, ic_inject=ics)
         else:
-            out = vec.step(a)
+            out = vec.step(a, ic_inject=ics)
         gs = {k: g[k][t] for k in ("done", "truncated", "nfev", "y", "reward", "obs")}
         d, _ = G.compare_step(name, t, norm, gs, out["y_pre_reset"], out["obs"], out["reward"], out["done"], out["truncated"], out["natt"])
         dn = g["done"][t].astype(bool)
