@@ -29,8 +29,8 @@ TRAFFIC_BYTES_PER_LAUNCH = 22.2e6         # measured DRAM read+write of one step
 
 
 def env_config():
-    from tests import goldutil as G
-    return G.cfg6()
+    from rl_rocket_b200.config import env_config_6dof
+    return env_config_6dof()
 
 
 # ----------------------------------------------------------------------------------------------- clocks

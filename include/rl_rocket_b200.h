@@ -32,6 +32,7 @@
 #ifndef RL_ROCKET_B200_H
 #define RL_ROCKET_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -165,6 +166,24 @@ int rlr_step_range(const RlrParams* p, int precision, int math_mode, RlrState st
 int rlr_rollout(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind,
                 int32_t T, float* obs_buf, float* reward_buf, uint8_t* done_buf, uint8_t* trunc_buf, float* last_obs,
                 unsigned long long* stats, int64_t n, int64_t env_offset, uint64_t seed, void* stream);
+
+/* Host-buffer pipeline: what DummyVecEnv.step_wait does on the host for one step (main_6DOF.py:71, main.py:105) -- take the actions
+ * from host memory, step, hand obs / reward / done back in host memory -- as ONE call that does not block, with `depth` slots so that
+ * the PCIe transfers of one step overlap the integration of the next (the step kernels of consecutive submits still run in order on
+ * compute_stream: the state dependency between steps is kept on the device).
+ *   rlr_pipe_submit(slot): H2D copy of h_actions (pinned) into d_actions on the pipe's copy stream; rlr_step on compute_stream with
+ *       `out` (its obs / reward / done must point into d_pack: obs at 0, reward at n*nobs*4, done at n*nobs*4 + n*4); D2H copy of
+ *       d_pack into h_pack (pinned) on the pipe's second copy stream.  The slot's buffers (h_actions, d_actions, d_pack, h_pack) are
+ *       caller-owned and must stay untouched until rlr_pipe_wait(slot) returns; a slot is resubmitted only after it was waited for.
+ *   rlr_pipe_wait(slot): blocks the host until the slot's result is in h_pack.
+ * Create / destroy on the device the environments live on. */
+typedef struct RlrHostPipe RlrHostPipe;
+int rlr_pipe_create(RlrHostPipe** pipe, int depth);
+int rlr_pipe_destroy(RlrHostPipe* pipe);
+int rlr_pipe_submit(RlrHostPipe* pipe, int slot, const RlrParams* p, int precision, int math_mode, RlrState st, const void* h_actions,
+                    void* d_actions, size_t action_bytes, int action_kind, RlrStepOut out, const void* d_pack, void* h_pack,
+                    size_t pack_bytes, int64_t n, int64_t env_offset, uint64_t seed, void* compute_stream);
+int rlr_pipe_wait(RlrHostPipe* pipe, int slot);
 
 /* FP64 / FP32 FMA roofline calibration: launches a dependent-chain FMA kernel, returns flops issued. */
 int rlr_fma_peak(int precision, int blocks, int threads, int iters, double* sink, double* flops_out, void* stream);

@@ -23,14 +23,14 @@ def __getattr__(name):
     raise AttributeError(name)
 
 
-def _register_gym_ids():
+def _register_gym_ids(prefix="rl_rocket_b200.envs"):
     try:
         from gym.envs.registration import register
     except Exception:  # noqa: BLE001 - gym absent: nothing to register
         return False
     for gid, cls in (("my_environment/Falcon3DOF-v0", "Rocket"), ("my_environment/Falcon6DOF-v0", "Rocket6DOF")):
         try:
-            register(id=gid, entry_point=f"rl_rocket_b200.envs:{cls}")
+            register(id=gid, entry_point=f"{prefix}:{cls}")
         except Exception:  # noqa: BLE001 - already registered
             pass
     return True

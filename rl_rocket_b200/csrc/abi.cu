@@ -61,6 +61,8 @@ static int check_state(const RlrState& st) {
     return RLR_OK;
 }
 
+extern "C" int rlr_set_error_(int code, const char* msg) { return fail(code, msg); }      // shared with host_pipe.cu (not in the public header)
+
 extern "C" {
 
 int rlr_abi_version(void) { return RLR_ABI_VERSION; }

@@ -58,6 +58,16 @@ RLR_DEV void phase_mark(int k) {
 #else
 #define RLR_PHASE(k)
 #endif
+// Development aid (-DRLR_WARP_TRACE=1): one record per warp of the last step launch -- SM id, global-timer start / end, and what
+// the warp carried (most RK45 attempts of a lane, ground event, finished lanes) -- to see which warps make the tail of the launch.
+#ifndef RLR_WARP_TRACE
+#define RLR_WARP_TRACE 0
+#endif
+#if RLR_WARP_TRACE
+__device__ unsigned long long g_warp_trace[8192 * 4];
+RLR_DEV unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+RLR_DEV unsigned smid_() { unsigned s; asm volatile("mov.u32 %0, %smid;" : "=r"(s)); return s; }
+#endif
 
 // Programmatic dependent launch (sm_90+): a step kernel lets the next kernel of the stream begin launching at once and itself waits
 // for its predecessor's completion only right before its first global access, so consecutive step launches (action repeat, graph
@@ -1721,6 +1731,9 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
     float obs[S::N];
     pdl_wait_for_predecessor();
     RLR_PHASE(-1);
+#if RLR_WARP_TRACE
+    const unsigned long long trace_t0 = globaltimer_ns();
+#endif
     if (active) {
         load_state<S>(gs, n, i, st);
         float u[3], a_thr;
@@ -1770,6 +1783,19 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
     if constexpr (S::N == 14) write_obs6_warp(p, out.obs, i, active, (const float(&)[14])obs, sK, stage_obs);
     accumulate_stats(out.stats, active, fl, ep_len, ep_ret);
     RLR_PHASE(7);                       // 7: obs / state stores, statistics
+#if RLR_WARP_TRACE
+    {
+        const unsigned m_att = __reduce_max_sync(0xffffffffu, (unsigned)fl.natt);
+        const unsigned n_ev = __popc(__ballot_sync(0xffffffffu, fl.status == 1)), n_fin = __popc(__ballot_sync(0xffffffffu, fl.done != 0));
+        const unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+        if ((threadIdx.x & 31) == 0 && w < 8192) {
+            g_warp_trace[w * 4 + 0] = smid_();
+            g_warp_trace[w * 4 + 1] = trace_t0;
+            g_warp_trace[w * 4 + 2] = globaltimer_ns();
+            g_warp_trace[w * 4 + 3] = m_att | (n_ev << 8) | (n_fin << 16);
+        }
+    }
+#endif
 }
 
 template <class S>

@@ -47,6 +47,15 @@ class _SingleEnv(spaces.GymEnv):
         self._episode = 0
         self.seed(spec.seed)
 
+    def _set_obs_mode(self, obs_mode):
+        """Observation-mode switch used by wrappers.GaudetStateObs: the batch of one is rebuilt around the modified spec."""
+        from .engine import RocketBatch
+        self._spec = self._spec.with_(obs_mode=obs_mode)
+        old = self._batch
+        self._batch = RocketBatch(self._spec, 1, device=old.device, seed=old.seed, debug_outputs=True,
+                                  math_mode="exact" if old.math_mode == 0 else "fast")
+        self.observation_space = spaces.Box(low=-1, high=1, shape=(self._spec.nobs,))
+
     # ---- gym API
     def seed(self, seed=42):
         """Keys the device-side Philox IC sampler (the reference seeds gym's RandomState here, rocket_env.py:478-480)."""
@@ -191,6 +200,8 @@ class Rocket(_SingleEnv):
         self.y = y
 
     def _format_obs(self, obs_f32, s_f32):
+        if self._spec.obs_mode == 1:
+            return obs_f32                                         # GaudetStateObs: np.float32 4-vector (wrappers.py:66)
         return s_f32 / self.state_normalizer                      # rocket_env.py:148, :175, :209-210: float64 from the f32 state
 
     def _physical_action(self, action):

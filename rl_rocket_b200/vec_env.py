@@ -7,7 +7,9 @@ get_attr / set_attr / env_method / env_is_wrapped / render / get_images) plus a 
 
     obs, reward, done = venv.step_tensor(actions_cuda)      # no host sync
     obs, reward, done = venv.step_host(actions_pinned)      # pinned host buffers in/out, one H2D + one D2H per step
+    h = venv.step_host_async(actions_pinned); ...; obs, reward, done = h.wait()     # the same, pipelined over `depth` slots
 """
+import ctypes as C
 import time
 
 import numpy as np
@@ -15,7 +17,8 @@ import torch
 
 from . import spaces
 from .config import DEFAULT_DISCRETE_TABLE, EnvSpec
-from .engine import RocketBatch
+from . import _native as N
+from .engine import RocketBatch, _ptr
 
 try:  # pragma: no cover - SB3 is absent from the build image
     from stable_baselines3.common.vec_env.base_vec_env import VecEnv as _VecEnvBase
@@ -40,10 +43,10 @@ class _LazyInfos(list):
 class RocketVecEnv(_VecEnvBase):
     def __init__(self, num_envs, dof=6, max_episode_steps=None, device="cuda:0", discrete_actions=False, discrete_table=None,
                  reward_annealing=False, math_mode="fast", env_offset=0, trace_indices=None, trace_capacity=4096, precision="f64",
-                 **env_kwargs):
+                 gaudet_obs=False, **env_kwargs):
         table = (discrete_table or DEFAULT_DISCRETE_TABLE) if discrete_actions else None
         self.spec = EnvSpec(dof, max_episode_steps=max_episode_steps or 0, reward_mode=1 if reward_annealing else 0,
-                            discrete_table=table, **env_kwargs)
+                            discrete_table=table, obs_mode="gaudet" if gaudet_obs else "state", **env_kwargs)
         self.batch = RocketBatch(self.spec, num_envs, device=device, math_mode=math_mode, env_offset=env_offset,
                                  debug_outputs=trace_indices is not None, precision=precision)
         self.trace = TrajectoryTrace(self.batch, trace_indices, trace_capacity) if trace_indices is not None else None
@@ -62,6 +65,8 @@ class RocketVecEnv(_VecEnvBase):
         self._h_rew = self._h_pack[n * no * 4:n * no * 4 + n * 4].view(torch.float32)
         self._h_done = self._h_pack[n * no * 4 + n * 4:]
         self._ot_host = None          # RlrStepOut with obs | reward | done in mapped pinned host memory (built on first use)
+        self._pipe = None             # host-buffer pipeline (rlr_pipe_*), built by the first step_host_async
+        self._fin_pack = None         # device staging of the finished episodes' info fields (step_wait)
         self._t_start = time.time()
         self._pending = False
         self.metadata = {"render.modes": []}
@@ -110,6 +115,24 @@ class RocketVecEnv(_VecEnvBase):
         torch.cuda.current_stream(self.device).synchronize()
         return self._h_obs, self._h_rew, self._h_done
 
+    # ---------------------------------------------------------------- pipelined host path
+    def step_host_async(self, actions_host, depth=2):
+        """Non-blocking `step_host`: enqueues H2D(actions) -> step kernel -> D2H(obs | reward | done) through the C ABI's host
+        pipeline (rlr_pipe_submit, one ctypes call) and returns a handle; `handle.wait()` blocks until this step's results are in
+        pinned host memory and returns (obs, reward, done) views of the slot's buffers -- valid until the slot is reused `depth`
+        submits later.  Consecutive submits keep their order on the device (step t + 1 integrates from step t's state) while the
+        PCIe transfers of step t overlap the integration of step t + 1: for open-loop action sources (random / scripted / action
+        repeat) or two environment groups stepped alternately.  `actions_host` must be pinned and stay untouched until wait()."""
+        if not torch.is_tensor(actions_host):
+            actions_host = torch.as_tensor(np.ascontiguousarray(actions_host))
+        a = actions_host.reshape(self._h_actions.shape)
+        if not (a.dtype == self._h_actions.dtype and a.is_contiguous() and a.is_pinned()):
+            raise ValueError("step_host_async needs a contiguous pinned host tensor of the action dtype (it is read asynchronously)")
+        b = self.batch
+        if self._pipe is None:
+            self._pipe = _HostPipe(self, depth)
+        return self._pipe.submit(a)
+
     def h2d_bytes_per_step(self):
         return self._h_actions.numel() * self._h_actions.element_size()
 
@@ -133,21 +156,27 @@ class RocketVecEnv(_VecEnvBase):
         self._pending = False
         obs, rew, done = self.step_host(self._h_actions)
         obs_np, rew_np, done_np = obs.numpy().copy(), rew.numpy().copy(), done.numpy().astype(bool)
-        infos = _LazyInfos([_EMPTY_INFO] * self.num_envs)
+        empty = {}                    # one fresh dict per step, shared by this step's non-terminal environments only
+        infos = _LazyInfos([empty] * self.num_envs)
         idx = np.nonzero(done_np)[0]
         if idx.size:
-            b = self.batch
+            # the finished episodes' info fields leave the device as ONE gathered float64 block (one D2H copy, one sync)
+            b, no = self.batch, self.spec.nobs
             sel = torch.as_tensor(idx, device=self.device)
-            term = b.terminal_obs[sel].cpu().numpy()
-            ret = b.fin_ret[sel].cpu().numpy()
-            length = b.fin_len[sel].cpu().numpy()
-            trunc = b.truncated[sel].cpu().numpy().astype(bool)
-            flags = b.flags[sel].cpu().numpy()
+            pack = torch.empty((idx.size, no + 4), dtype=torch.float64, device=self.device)
+            pack[:, :no] = b.terminal_obs[sel]
+            pack[:, no] = b.fin_ret[sel]
+            pack[:, no + 1] = b.fin_len[sel]
+            pack[:, no + 2] = b.truncated[sel]
+            pack[:, no + 3] = b.flags[sel]
+            h = pack.cpu().numpy()
+            term = h[:, :no].astype(np.float32)                # exact: the values were float32
             now = round(time.time() - self._t_start, 6)
             for j, i in enumerate(idx):
-                infos[i] = {"terminal_observation": term[j], "TimeLimit.truncated": bool(trunc[j]),
-                            "episode": {"r": round(float(ret[j]), 6), "l": int(length[j]), "t": now},
-                            "bounds_violation": bool(flags[j] & 1), "landed": bool(flags[j] & 2), "is_done": True}
+                fl = int(h[j, no + 3])
+                infos[i] = {"terminal_observation": term[j], "TimeLimit.truncated": bool(h[j, no + 2]),
+                            "episode": {"r": round(float(h[j, no]), 6), "l": int(h[j, no + 1]), "t": now},
+                            "bounds_violation": bool(fl & 1), "landed": bool(fl & 2), "is_done": True}
         return obs_np, rew_np, done_np, infos
 
     def close(self):
@@ -155,7 +184,7 @@ class RocketVecEnv(_VecEnvBase):
 
     def seed(self, seed=None):
         seed = 0 if seed is None else int(seed)
-        self.batch.seed = seed
+        self.batch.reseed(seed)            # re-keys the reset RNG and restarts the episode numbering: seed(s) + reset() reproduces
         return [seed + i for i in range(self.num_envs)]
 
     def _indices(self, indices):
@@ -198,7 +227,65 @@ class RocketVecEnv(_VecEnvBase):
         return self.batch.read_stats(reset=reset)
 
 
-_EMPTY_INFO = {}
+class _HostPipe:
+    """`depth` slots of (device actions, device obs|reward|done pack, pinned host pack) around the C ABI's rlr_pipe_*."""
+
+    def __init__(self, venv, depth):
+        b = venv.batch
+        self.venv, self.depth, self.turn = venv, int(depth), 0
+        self.lib = b.lib
+        n, no = b.n, b.spec.nobs
+        self.kind = N.ACT_DISCRETE if venv.discrete else N.ACT_NORMALIZED
+        self.handle = C.c_void_p()
+        with torch.cuda.device(b.device):
+            N.check(self.lib.rlr_pipe_create(C.byref(self.handle), self.depth))
+        self.slots = []
+        for _ in range(self.depth):
+            d_act = torch.zeros_like(venv._h_actions, device=b.device)
+            d_pack = torch.zeros_like(b.out_pack)
+            h_pack = torch.zeros_like(b.out_pack, device="cpu").pin_memory()
+            obs = d_pack[:n * no * 4].view(torch.float32).view(n, no)
+            rew = d_pack[n * no * 4:n * no * 4 + n * 4].view(torch.float32)
+            done = d_pack[n * no * 4 + n * 4:]
+            out = b.step_out_struct(obs, rew, done)
+            views = (h_pack[:n * no * 4].view(torch.float32).view(n, no), h_pack[n * no * 4:n * no * 4 + n * 4].view(torch.float32),
+                     h_pack[n * no * 4 + n * 4:])
+            self.slots.append((d_act, d_pack, h_pack, out, views))
+
+    def submit(self, a):
+        b = self.venv.batch
+        s = self.turn % self.depth
+        self.turn += 1
+        d_act, d_pack, h_pack, out, views = self.slots[s]
+        prev = torch.cuda.current_device()
+        if prev != b._dev_index:
+            torch.cuda.set_device(b._dev_index)
+        rc = self.lib.rlr_pipe_submit(self.handle, s, b._params_ref, b.precision, b.math_mode, b._st, a.data_ptr(), d_act.data_ptr(),
+                                      a.numel() * a.element_size(), self.kind, out, d_pack.data_ptr(), h_pack.data_ptr(), h_pack.numel(),
+                                      b.n, b.env_offset, b.seed, torch.cuda.current_stream(b._dev_index).cuda_stream)
+        if prev != b._dev_index:
+            torch.cuda.set_device(prev)
+        if rc:
+            N.check(rc)
+        b.launches += 1
+        return HostStepHandle(self, s, views, a)
+
+    def __del__(self):
+        try:
+            self.lib.rlr_pipe_destroy(self.handle)
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
+class HostStepHandle:
+    def __init__(self, pipe, slot, views, actions):
+        self._pipe, self._slot, self._views, self._actions = pipe, slot, views, actions      # (keeps the pinned actions alive)
+
+    def wait(self):
+        rc = self._pipe.lib.rlr_pipe_wait(self._pipe.handle, self._slot)
+        if rc:
+            N.check(rc)
+        return self._views
 
 
 class TrajectoryTrace:

@@ -281,6 +281,7 @@ def test_step_is_cuda_graph_capturable():
     with torch.cuda.stream(side):                       # warm-up on the capture stream (launch geometry / attribute queries happen here)
         graphed.step_tensor(a[0])
     side.synchronize()
+    graphed.reseed(9)                                   # a second reset() alone would move on to the next episode's initial conditions
     graphed.reset()
     obs_hist = torch.zeros((T, N, 14), device="cuda")
     g = torch.cuda.CUDAGraph()
@@ -299,3 +300,122 @@ def test_step_is_cuda_graph_capturable():
     for t in range(T):
         eager.step_tensor(a[t])
     assert torch.equal(eager.y, graphed.y)
+
+
+@pytest.mark.parametrize("depth", [2, 3])
+def test_step_host_async_pipeline_equals_synchronous_path(depth):
+    """RocketVecEnv.step_host_async (rlr_pipe_*: H2D / kernel / D2H on three streams, `depth` slots) returns, step for step, what the
+    synchronous step_host returns -- including when the host runs `depth` submits ahead of the results it collects."""
+    from rl_rocket_b200.vec_env import RocketVecEnv
+    N, T = 5000, 60
+    cfg = G.cfg6()
+    v1 = RocketVecEnv(N, dof=6, max_episode_steps=25, **cfg)
+    v2 = RocketVecEnv(N, dof=6, max_episode_steps=25, **cfg)
+    v1.reset(); v2.reset()
+    rng = np.random.RandomState(1)
+    acts = [torch.as_tensor(rng.uniform(-1, 1, (N, 3)).astype(np.float32)).pin_memory() for _ in range(T)]
+    ref = []
+    for t in range(T):
+        o, r, d = v2.step_host(acts[t], zero_copy=False)
+        ref.append((o.clone(), r.clone(), d.clone()))
+    pending = []
+    got = []
+    for t in range(T):
+        pending.append(v1.step_host_async(acts[t], depth=depth))
+        if len(pending) == depth:                       # collect the oldest before its slot is resubmitted
+            got.append(tuple(x.clone() for x in pending.pop(0).wait()))
+    while pending:
+        got.append(tuple(x.clone() for x in pending.pop(0).wait()))
+    assert len(got) == T
+    for t in range(T):
+        assert torch.equal(got[t][0], ref[t][0]) and torch.equal(got[t][1], ref[t][1]) and torch.equal(got[t][2], ref[t][2]), t
+    assert v1.episode_stats() == v2.episode_stats() and v1.episode_stats()["done"] > 0
+    with pytest.raises(ValueError):
+        v1.step_host_async(torch.zeros((N, 3)))         # not pinned
+
+
+def test_vecenv_reset_draws_fresh_initial_conditions_and_seed_reproduces():
+    """Every reset() samples new initial conditions (init_space.sample(), rocket_env.py:142, :672); seed(s) + reset() reproduces."""
+    from rl_rocket_b200.vec_env import RocketVecEnv
+    v = RocketVecEnv(256, dof=6, max_episode_steps=800, **G.cfg6())
+    v.seed(7)
+    o1 = v.reset()
+    o2 = v.reset()
+    assert not np.array_equal(o1, o2)
+    v.step(np.zeros((256, 3), np.float32))
+    o3 = v.reset()
+    assert not np.array_equal(o3, o1) and not np.array_equal(o3, o2)
+    v.seed(7)
+    assert np.array_equal(v.reset(), o1) and np.array_equal(v.reset(), o2)
+    # infos of non-terminal environments: a fresh dict per step (writing into one must not leak into later steps)
+    _, _, done, infos = v.step(np.zeros((256, 3), np.float32))
+    infos[0]["mine"] = 1
+    _, _, done, infos2 = v.step(np.zeros((256, 3), np.float32))
+    assert "mine" not in infos2[0]
+
+
+def test_vecenv_gaudet_observation_matches_golden():
+    """RocketVecEnv(gaudet_obs=True) (RLR_OBS_GAUDET) against the corrected GaudetStateObs wrapper over the live reference."""
+    from rl_rocket_b200.vec_env import RocketVecEnv
+    for name in ("traj_3dof_gaudet.npz", "traj_3dof_default_gaudet.npz"):
+        dof, cfgf, tl, mode, akind = G.TRAJ[name]
+        g = G.load(name)
+        T, N = g["done"].shape
+        v = RocketVecEnv(N, dof=3, max_episode_steps=tl, math_mode="exact", gaudet_obs=True, **cfgf())
+        v.seed(int(g["seed"]))
+        assert v.observation_space.shape == (4,)
+        obs = v.reset()
+        assert obs.shape == (N, 4) and np.abs(obs.astype(float) - g["obs0"]).max() <= 1e-6 * np.maximum(1, np.abs(g["obs0"])).max()
+        for t in range(T):
+            obs, rew, done, infos = v.step(g["actions"][t])
+            assert np.array_equal(done, g["done"][t].astype(bool))
+            tol = 1e-6 * np.maximum(1.0, np.abs(g["obs"][t]))
+            assert (np.abs(obs.astype(float) - g["obs"][t]) <= tol).all(), (name, t)
+            for i in np.nonzero(done)[0]:
+                assert (np.abs(infos[i]["terminal_observation"].astype(float) - g["terminal_obs"][t][i]) <= 1e-6 * np.maximum(1, np.abs(g["terminal_obs"][t][i]))).all()
+
+
+def test_discrete_actions_with_reward_annealing_matches_golden():
+    """DiscreteActions3DOF(RewardAnnealing(Rocket)) (main.py:139-146): the annealed thrust penalty sees the table row."""
+    from rl_rocket_b200.vec_env import RocketVecEnv
+    g = G.load("traj_3dof_discrete_annealing.npz")
+    T, N = g["done"].shape
+    v = RocketVecEnv(N, dof=3, max_episode_steps=3000, discrete_actions=True, reward_annealing=True, math_mode="exact", **G.cfg3())
+    v.seed(int(g["seed"]))
+    v.reset()
+    for t in range(T):
+        obs, rew, done, infos = v.step(g["actions"][t])
+        assert np.array_equal(done, g["done"][t].astype(bool))
+        assert np.abs(rew.astype(float) - g["reward"][t]).max() <= 1e-6 * max(1.0, np.abs(g["reward"][t]).max())
+    assert len({float(x) for x in np.round(g["reward"], 9).ravel()}) >= 2      # throttle -1 rows (0) and throttle +1 rows (-2 xi) both occur
+
+
+def test_3dof_vtarg_output_matches_oracle():
+    """SURVEY A14 on the GPU: the step path's vtarg output of the 3DOF kernel against the C oracle's or_env_step on the same pre-step
+    states (KAT-4, tests/test_oracle_golden.py, pins the oracle's _compute_vtarg to the reference's test_vtarg.py grid)."""
+    import ctypes as C
+    from oracle import c_oracle as O
+    from rl_rocket_b200.config import EnvSpec
+    from rl_rocket_b200.engine import RocketBatch
+    N, T = 512, 40
+    lib = O.lib()
+    for cfg, tl in ((G.cfg3(), 3000), (G.cfg3_default(), 2000)):
+        for mm in ("exact", "fast"):
+            spec = EnvSpec(3, max_episode_steps=tl, **cfg)
+            p = O.make_params(3, max_episode_steps=tl, **cfg)
+            env = RocketBatch(spec, N, seed=3, math_mode=mm, debug_outputs=True)
+            env.reset()
+            rng = np.random.RandomState(5)
+            for t in range(T):
+                a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+                y0, k0, v0 = env.y.cpu().numpy().T.copy(), env.k.cpu().numpy(), env.v0.cpu().numpy()
+                env.step_tensor(torch.as_tensor(a).cuda())
+                vt = env.vtarg.cpu().numpy()
+                ref = np.zeros((N, 4))
+                obs, r, fl = np.zeros(14, np.float32), C.c_double(0), np.zeros(6, np.int32)
+                for i in range(N):
+                    yy = y0[i].copy()
+                    lib.or_env_step(C.byref(p), O._p(yy, C.c_double), C.c_int(int(k0[i])), C.c_float(float(v0[i])), O._p(a[i], C.c_float), C.c_int(0),
+                                    O._p(obs, C.c_float), C.byref(r), None, O._p(fl, C.c_int), O._p(ref[i], C.c_double))
+                scale = np.maximum(1.0, np.abs(ref.T))
+                assert (np.abs(vt - ref.T) <= 1e-9 * scale).all(), (mm, t, np.abs(vt - ref.T).max())

@@ -34,19 +34,22 @@ def test_golden_trajectories(name, math_mode):
     g = G.load(name)
     T, N = g["done"].shape
     env = RocketBatch(spec, N, seed=int(g["seed"]), math_mode=math_mode, debug_outputs=True)
-    obs0 = env.reset().cpu().numpy()
+    ics = torch.as_tensor(g["ics"]).cuda() if "ics" in g.files else None      # crafted cases: every episode of env i restarts from ics[i]
+    obs0 = env.reset(ic=ics).cpu().numpy()
     assert np.abs(obs0.astype(float) - g["obs0"]).max() <= G.OBS_TOL
     norm = spec.state_normalizer
     worst = 0.0
     for t in range(T):
         a = torch.as_tensor(g["actions"][t]).cuda()
-        obs, rew, done = env.step_tensor(a)
+        obs, rew, done = env.step_tensor(a, ic_inject=ics)
         gs = {k: g[k][t] for k in ("done", "truncated", "nfev", "y", "reward", "obs")}
         d, _ = G.compare_step(f"{name}/{math_mode}", t, norm, gs, env.y_pre_reset.cpu().numpy(), obs.cpu().numpy(),
                               env.reward64.cpu().numpy(), done.cpu().numpy(), env.truncated.cpu().numpy(), env.natt.cpu().numpy())
         dn = g["done"][t].astype(bool)
         assert np.abs(env.terminal_obs.cpu().numpy()[dn].astype(float) - g["terminal_obs"][t][dn]).max(initial=0) <= G.OBS_TOL
         worst = max(worst, d)
+        if "rew_goal" in g.files:      # the success branch (rocket_env.py:1040-1061 / :449-476): landed flag bit-exact
+            assert np.array_equal(((env.flags.cpu().numpy() >> 1) & 1).astype(bool), g["rew_goal"][t] != 0), f"{name} step {t}: landed flags differ"
     print(f"{name} [{math_mode}] worst normalised state deviation {worst:.3e}")
 
 

@@ -122,6 +122,18 @@ def test_f32_helpers_match_numpy():
     lib = O.lib()
     assert all(np.float32(lib.or_np_sinf(float(x))) == np.sin(x) for x in xs[:5000])
     assert all(np.float32(lib.or_np_cosf(float(x))) == np.cos(x) for x in xs[:5000])
+    # beyond pi/4 (the environments never clip the action: |gimbal| = |a| * 20 deg): numpy's Cody-Waite range reduction, bit-exact up to
+    # its limit 71476.0625 rad (|action| ~ 2e5).  Beyond that numpy calls glibc's sinf / cosf (< 1 ulp, not correctly rounded); the
+    # restatement returns the correctly rounded value there: within one float32 ulp, outside the bit-exact contract.
+    wide = np.concatenate([rng.uniform(-1.1, 1.1, 4000), rng.uniform(-64, 64, 4000), rng.uniform(-7e4, 7e4, 2000),
+                           np.float32([np.pi / 4, -np.pi / 4, np.pi / 2, np.pi, 3 * np.pi / 4, 71476.0625, -71476.0625])]).astype(np.float32)
+    s_or = np.float32([lib.or_np_sinf(float(x)) for x in wide])
+    c_or = np.float32([lib.or_np_cosf(float(x)) for x in wide])
+    assert np.array_equal(s_or, np.sin(wide)) and np.array_equal(c_or, np.cos(wide))
+    far = rng.uniform(-2e6, 2e6, 2000).astype(np.float32)
+    s_far = np.float32([lib.or_np_sinf(float(x)) for x in far])
+    c_far = np.float32([lib.or_np_cosf(float(x)) for x in far])
+    assert np.abs(s_far - np.sin(far)).max() <= 6e-8 and np.abs(c_far - np.cos(far)).max() <= 6e-8
 
 
 def test_philox_known_answer():
