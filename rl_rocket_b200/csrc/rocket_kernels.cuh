@@ -60,6 +60,13 @@ RLR_DEV void phase_mark(int k) {
 #endif
 // Development aid (-DRLR_WARP_TRACE=1): one record per warp of the last step launch -- SM id, global-timer start / end, and what
 // the warp carried (most RK45 attempts of a lane, ground event, finished lanes) -- to see which warps make the tail of the launch.
+// tuning switches (A/B builds): 1 = stage 6 peeled and fused with the error / quadrature sums; 1 = dead scalars parked in shared memory
+#ifndef RLR_FUSED_ERR
+#define RLR_FUSED_ERR 1
+#endif
+#ifndef RLR_PARK
+#define RLR_PARK 1
+#endif
 #ifndef RLR_WARP_TRACE
 #define RLR_WARP_TRACE 0
 #endif
@@ -665,7 +672,22 @@ RLR_DEV void rhs6r(const Sys6::Ctx& c, const double (&q)[4], const double (&wv)[
 
 constexpr int BS6 = 64;                                   // threads per block of the 6DOF kernels (compile time: LDS offsets are immediates)
 constexpr int KROW = 5 * BS6;                             // double2 slots between consecutive stages (10 doubles per thread and stage)
-constexpr size_t SMEM6_BYTES = 6 * KROW * sizeof(double2); // 30 KB per block
+constexpr size_t SMEM6_K_BYTES = 6 * KROW * sizeof(double2);   // stage matrix: 30 KB per block
+// ... followed by a 20-byte-per-thread parking area for the per-environment scalars that are dead during the solve (running return,
+// step counter, episode counter, |v| of the initial condition).  At the 128-register cap ptxas spilled them to local memory, and with
+// 210 KB of the SM's 256 KB configured as shared memory the 448 threads' stack frames do not fit what is left of L1: the reloads in
+// the epilogue were L2 round trips (6.5 % of the step kernel's stall samples, profiles/r01e).  7 blocks x (32 000 + 1 024) B still fit an SM.
+constexpr size_t SMEM6_BYTES = SMEM6_K_BYTES + BS6 * (sizeof(double) + 3 * sizeof(int32_t));
+struct Park6 {
+    volatile double* ep_ret; volatile int32_t* k; volatile int32_t* episode; volatile float* v0;
+    RLR_DEV explicit Park6(double* sK) {
+        char* base = reinterpret_cast<char*>(sK) + SMEM6_K_BYTES;
+        ep_ret = reinterpret_cast<double*>(base) + threadIdx.x;
+        k = reinterpret_cast<int32_t*>(base + BS6 * 8) + threadIdx.x;
+        episode = reinterpret_cast<int32_t*>(base + BS6 * 12) + threadIdx.x;
+        v0 = reinterpret_cast<float*>(base + BS6 * 16) + threadIdx.x;
+    }
+};
 
 // Terminal ground event of the 6DOF solve (ivp.py:678-699): dense output Q = K^T P (rk.py:554-565, :715-737), Brent root on the
 // height polynomial, final state y(t_e).  buf = [y(14) | K6(10) | v_new(3) | dm, t_old, h, t_new]; y(t_e) is written to buf[0..13].
@@ -850,6 +872,7 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
 #pragma unroll
         for (int i = 0; i < 3; ++i) { aB[i] = y[3 + i] * B0; aE[i] = y[3 + i] * E0; }
 #endif
+#if RLR_EXACT || !RLR_FUSED_ERR
         // ---- rk_step (rk.py:14-71); stage 6 is y_new (row 6 of c_RKA = B).
         // Fast build: d(omega_x)/dt is identically zero (J_y == J_z, see rhs6r), so component 7 of the stage matrix is skipped and
         // omega_x keeps its value; dm is constant, so the mass stage value is m + (c_s h) dm.
@@ -983,6 +1006,107 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
         const double err = RLR_DIV(sqrt_(ssum), sqrt(14.0));
 #else
         // the error weights sum to zero: a constant derivative (the mass) contributes |dm| * O(1e-17) -- dropped
+        const double err = sqrtc_(ssum) * RLR_INV_RS14;
+#endif
+#else
+        // ---- rk_step (rk.py:14-71), fast build.  d(omega_x)/dt is identically zero (J_y == J_z, see rhs6r), so component 7 of the
+        // stage matrix is skipped and omega_x keeps its value; dm is constant, so the mass stage value is m + (c_s h) dm.
+        // Stages 1..5 run in a rolled loop (one inlined right-hand side); rows 1 .. s-1 of the stage sum are unrolled behind
+        // warp-uniform guards, so every shared-memory / constant-bank address is base + immediate.
+#define RLR_LIVE(cc) ((cc) != 7)
+#pragma unroll 1
+        for (int s = 1; s <= 5; ++s) {
+            double acc[10];
+            const double a0 = c_RKA[s][0];
+#pragma unroll
+            for (int p = 0; p < 5; ++p) {
+                const double2 k2 = KS2(0, p);
+                acc[2 * p] = k2.x * a0;
+                if (RLR_LIVE(2 * p + 1)) acc[2 * p + 1] = k2.y * a0;
+            }
+#pragma unroll
+            for (int j = 1; j <= 4; ++j) {
+                if (j < s) {
+                    const double aj = c_RKA[s][j];
+#pragma unroll
+                    for (int p = 0; p < 5; ++p) {
+                        const double2 k2 = KS2(j, p);
+                        acc[2 * p] += k2.x * aj;
+                        if (RLR_LIVE(2 * p + 1)) acc[2 * p + 1] += k2.y * aj;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sv[i] = y[3 + i] + acc[i] * h;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sq[i] = y[6 + i] + acc[3 + i] * h;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sw[i] = RLR_LIVE(7 + i) ? y[10 + i] + acc[7 + i] * h : y[10 + i];
+            sm = y[13] + (c_RKC[s] * h) * c.dm;
+            rhs6r(c, sq, sw, sm, kk);
+            double2* ko = sKt + s * KROW;
+#pragma unroll
+            for (int p = 0; p < 5; ++p) ko[p * BS6] = make_double2(kk[2 * p], kk[2 * p + 1]);
+        }
+        // ---- stage 6 is y_new (row 6 of the tableau is B; b_1 = 0, so row 1 is not read), straight-line and fused with everything
+        // else that reads the stage matrix: ONE pass over rows 0, 2, 3, 4, 5 feeds
+        //   * the B-weighted sum (y_new),
+        //   * the E-weighted sum of the error estimate (rk.py:101-107; K6 = f(y_new) is added from registers after the right-hand side),
+        //   * the position rows by quadrature of the acceleration rows instead of per-stage accumulators:
+        //       sum_s b_s v_s = v + h sum_j beta_j K_j,  beta_j = sum_s b_s a_sj = b_j (1 - c_j)  (= 0 for j = 1, 5), and
+        //       sum_s e_s v_s = h sum_j eps_j K_j  because the error weights sum to zero (eps_j = sum_s e_s a_sj + e_6 b_j).
+        // (Before: the error norm re-read five rows per attempt -- 16 % of the kernel's shared-memory wavefronts, and the shared-memory
+        // pipe is ~75 % busy while the warps of an SM are in their RK attempts.)
+        constexpr double BT0 = 35.0 / 384, BT2 = 50.0 / 159, BT3 = 25.0 / 192, BT4 = -243.0 / 6784;
+        constexpr double EP0 = -611.0 / 230400, EP2 = 514.0 / 83475, EP3 = -391.0 / 38400, EP4 = 4617.0 / 1356800, EP5 = 11.0 / 3360;
+        double ae[10], sb[3], se[3];
+        {
+            double acc[10];
+#pragma unroll
+            for (int p = 0; p < 5; ++p) {
+                const double2 k0 = KS2(0, p), k2 = KS2(2, p), k3 = KS2(3, p), k4 = KS2(4, p), k5 = KS2(5, p);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int cc = 2 * p + hh;
+                    if (!RLR_LIVE(cc)) continue;
+                    const double c0 = hh ? k0.y : k0.x, c2 = hh ? k2.y : k2.x, c3 = hh ? k3.y : k3.x, c4 = hh ? k4.y : k4.x, c5 = hh ? k5.y : k5.x;
+                    acc[cc] = (((c0 * B0 + c2 * B2) + c3 * B3) + c4 * B4) + c5 * B5;
+                    ae[cc] = (((c0 * E0 + c2 * E2) + c3 * E3) + c4 * E4) + c5 * E5;
+                    if (cc < 3) {
+                        sb[cc] = ((c0 * BT0 + c2 * BT2) + c3 * BT3) + c4 * BT4;
+                        se[cc] = (((c0 * EP0 + c2 * EP2) + c3 * EP3) + c4 * EP4) + c5 * EP5;
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sv[i] = y[3 + i] + acc[i] * h;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sq[i] = y[6 + i] + acc[3 + i] * h;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) sw[i] = RLR_LIVE(7 + i) ? y[10 + i] + acc[7 + i] * h : y[10 + i];
+            sm = y[13] + h * c.dm;
+        }
+        rhs6r(c, sq, sw, sm, kk);
+        // ---- error norm (rk.py:101-107): components in index order r, v, q, w (the error weights sum to zero: a constant derivative
+        // -- the mass -- contributes |dm| * O(1e-17), dropped)
+        double rn[3];
+        double ssum = 0.0;
+#define RLR_ERR_TERM(num, yo, yn) ((num) * rcp1_(fma(absmax_(yo, yn), rtol, atol)))
+        const double hsq = h * h;
+#pragma unroll
+        for (int cc = 0; cc < 10; ++cc) {
+            if (!RLR_LIVE(cc)) continue;          // K rows of omega_x are exactly zero
+            const double yo = y[3 + cc];
+            const double yn = (cc < 3) ? sv[cc] : ((cc < 7) ? sq[cc - 3] : sw[cc - 7]);
+            const double es = ae[cc] + kk[cc] * E6;
+            const double e = RLR_ERR_TERM(es * h, yo, yn);
+            ssum += e * e;
+            if (cc < 3) {          // the position component integrated from this acceleration row
+                rn[cc] = y[cc] + (h * y[3 + cc] + hsq * sb[cc]);
+                const double er = RLR_ERR_TERM(se[cc] * hsq, y[cc], rn[cc]);
+                ssum += er * er;
+            }
+        }
         const double err = sqrtc_(ssum) * RLR_INV_RS14;
 #endif
 #undef RLR_ERR_TERM
@@ -1554,7 +1678,16 @@ RLR_DEV void env_step(const RlrParams& p, EnvState<S>& st, const float (&u)[3], 
     const double t = (double)((long long)st.k * (long long)p.dt_ms) / 1000.0;   // round(t + dt, 3)  (simulator.py:245)
     int natt;
     int status;
-    if constexpr (S::N == 14) status = rk45_solve6(c, t, t + p.dt, st.y, natt, reinterpret_cast<double2*>(sK) + threadIdx.x);
+    if constexpr (S::N == 14) {
+#if RLR_PARK
+        const Park6 park(sK);
+        *park.ep_ret = st.ep_ret; *park.k = st.k; *park.episode = st.episode; *park.v0 = st.v0;
+#endif
+        status = rk45_solve6(c, t, t + p.dt, st.y, natt, reinterpret_cast<double2*>(sK) + threadIdx.x);
+#if RLR_PARK
+        st.ep_ret = *park.ep_ret; st.k = *park.k; st.episode = *park.episode; st.v0 = *park.v0;
+#endif
+    }
 #if RLR_EXACT
     else status = rk45_solve<S>(c, t, t + p.dt, st.y, natt);
 #else

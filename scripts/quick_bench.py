@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from rl_rocket_b200.config import EnvSpec
 from rl_rocket_b200.engine import RocketBatch
-from tests import goldutil as G
+from rl_rocket_b200.config import env_config_6dof, env_config_3dof
 
 def timeit(fn, n):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -20,7 +20,7 @@ prec = os.environ.get("QB_PREC", "f64")
 res = {}
 for N in sizes:
     for mode in modes:
-        spec = EnvSpec(6, max_episode_steps=800, **G.cfg6())
+        spec = EnvSpec(6, max_episode_steps=800, **env_config_6dof())
         env = RocketBatch(spec, N, seed=1, math_mode=mode, precision=prec)
         env.reset()
         T = 300
@@ -31,13 +31,24 @@ for N in sizes:
         ms = timeit(lambda: env.step_tensor(a[next(it)]), 150)
         st = env.read_stats(reset=True)
         flops = 540 * st["steps"] + 1530 * st["attempts"]
+        if os.environ.get("QB_FLUSH", "1") == "1":       # what bench.py times: one launch per event pair, L2 evicted in between
+            flush = torch.zeros(64 * 1024 * 1024, device="cuda"); sink = torch.zeros(1, device="cuda")
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(100)]
+            for rep in range(2):
+                for t in range(100):
+                    torch.sum(flush, dim=(0,), keepdim=True, out=sink)
+                    ev[t][0].record(); env.step_tensor(a[50 + t]); ev[t][1].record()
+                torch.cuda.synchronize()
+            fl = sorted(x.elapsed_time(y) for x, y in ev)
+            print(f"[{tag}] {prec} step {mode} N={N} flushed, per-launch event pairs: mean {sum(fl)/len(fl)*1e3:.1f} us  median {fl[50]*1e3:.1f} us  min {fl[0]*1e3:.1f} us", flush=True)
+            env.read_stats(reset=True)
         print(f"[{tag}] {prec} step {mode} N={N}: {ms*1e3:.1f} us/step  {N/ms*1e3:.3e} env-steps/s  att/step {st['attempts']/st['steps']:.3f}  alg {flops/150/ms/1e9:.2f} Tflop/s", flush=True)
         env.rollout(a[:20]); torch.cuda.synchronize()      # first launch: lazy module load + local-memory sizing
         ms2 = timeit(lambda: env.rollout(a[:100]), 3) / 100
         print(f"[{tag}] {prec} rollout {mode} N={N}: {ms2*1e3:.1f} us/step  {N/ms2*1e3:.3e} env-steps/s", flush=True)
         res[f"{mode}_{N}"] = dict(step_us=ms * 1e3, rollout_us=ms2 * 1e3)
 if os.environ.get("QB_3DOF"):
-    spec = EnvSpec(3, max_episode_steps=3000, **G.cfg3())
+    spec = EnvSpec(3, max_episode_steps=3000, **env_config_3dof())
     for N in (4096, 65536):
         env = RocketBatch(spec, N, seed=1); env.reset()
         a = torch.rand((200, N, 2), device="cuda") * 2 - 1
