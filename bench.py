@@ -98,7 +98,7 @@ def run_reference(args):
             "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- ours
@@ -134,6 +134,10 @@ def run_ours(args):
     flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev) if args.l2_flush else None
     flush_sink = torch.zeros(1, dtype=torch.float32, device=dev)
     stat_gather = torch.zeros((world, 8), dtype=torch.int64, device=dev) if world > 1 else None
+    exchange = None
+    if world > 1:
+        from rl_rocket_b200.distributed import StatsExchange
+        exchange = StatsExchange(dev)            # NVLink peer-memory exchange (rlr_exchange_*); NCCL all-gather if it cannot be mapped
 
     def barrier():
         if world > 1:
@@ -151,8 +155,9 @@ def run_ours(args):
         if flush is not None:     # the flush kernel is warmed up too (lazy module load), and keeps the host ahead of the device queue
             torch.sum(flush, dim=(0,), keepdim=True, out=flush_sink)
         env.step_tensor(actions[t])
-    if world > 1:        # warm-up of the collective too (the first NCCL all-gather sets up its channels: milliseconds)
+    if world > 1:        # warm-up of the exchange too (first launch: module load; the NCCL fallback sets up its channels: milliseconds)
         for _ in range(3):
+            exchange.all_gather(env.stats)
             dist.all_gather_into_tensor(stat_gather, env.stats.unsqueeze(0))
     env.read_stats(reset=True)
     launches0 = env.launches
@@ -165,10 +170,10 @@ def run_ours(args):
         ev[t][0].record()
         env.step_tensor(actions[W + t])
         ev[t][1].record()
-    # per-rollout exchange of returns / done counts (NCCL all-gather of the 8-slot statistics record), timed
+    # per-rollout exchange of returns / done counts (all-gather of the 8-slot statistics record), timed
     ev[K][0].record()
     if world > 1:
-        dist.all_gather_into_tensor(stat_gather, env.stats.unsqueeze(0))
+        stat_gather = exchange.all_gather(env.stats)
     ev[K][1].record()
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
@@ -190,7 +195,9 @@ def run_ours(args):
     value = n * world * K / (max_ms * 1e-3)
 
     # ---- end to end through the public VecEnv API with HOST buffers (pinned): H2D of the actions + D2H of obs / reward / done inside
-    # the timed region, every step, on EVERY rank; whole-job value = all ranks' env-steps / the slowest rank's wall time
+    # the timed region, every step, on EVERY rank; whole-job value = all ranks' env-steps / the slowest rank's wall time.
+    # Headline: RocketVecEnv.step_host_async (C ABI rlr_pipe_submit / rlr_pipe_wait, two slots): the host hands over step t + 1's
+    # actions while step t's results are still crossing PCIe, and reads every step's result (done count) before reusing its slot.
     venv = RocketVecEnv(n, dof=6, max_episode_steps=800, device=dev, math_mode=args.math, env_offset=rank * n, **cfg)
     venv.reset_tensor()
     for t in range(PREP_STEPS):
@@ -204,14 +211,58 @@ def run_ours(args):
     for t in range(Ke):
         venv.step_host(h_actions[t])
     torch.cuda.synchronize(dev)
+    sync_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    D = max(2, args.e2e_depth)
+    pend = [venv.step_host_async(h_actions[t % Ke], depth=D) for t in range(D)]   # warm-up of the pipeline (stream / event creation)
+    for h in pend:
+        h.wait()
+    barrier()
+    done_seen = 0
+    t0 = time.perf_counter()
+    pend = []
+    for t in range(Ke):
+        pend.append(venv.step_host_async(h_actions[t]))
+        if len(pend) == D:
+            o_, r_, d_ = pend.pop(0).wait()
+            done_seen += int(d_[0])                    # the host reads the step's result
+    while pend:
+        o_, r_, d_ = pend.pop(0).wait()
+        done_seen += int(d_[0])
+    torch.cuda.synchronize(dev)
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    # PCIe ceiling of this box, measured the same way on every rank at once: the step's D2H bytes and H2D bytes as plain
+    # cudaMemcpyAsync on two streams, back to back, no kernel
+    d_pack, h_pack = venv.batch.out_pack, venv._h_pack
+    d_act = torch.empty_like(h_actions[0], device=dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    reps = 100
+    for rep in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        for t in range(reps):
+            with torch.cuda.stream(s_out):
+                h_pack.copy_(d_pack, non_blocking=True)
+            with torch.cuda.stream(s_in):
+                d_act.copy_(h_actions[t % Ke], non_blocking=True)
+        s_in.synchronize(); s_out.synchronize()
+        pcie_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        for x in (sync_s, e2e_s, pcie_s):
+            dist.all_reduce(x, op=dist.ReduceOp.MAX)
     e2e = n * world * Ke / float(e2e_s.item())
+    e2e_sync = n * world * Ke / float(sync_s.item())
+    pcie_ceiling = n * world * reps / float(pcie_s.item())
+    d2h_gbs = venv.d2h_bytes_per_step() * world * reps / float(pcie_s.item()) / 1e9
     e2e_d = {"value": e2e, "unit": "env-steps/s", "h2d_bytes_per_step": venv.h2d_bytes_per_step() * world,
              "d2h_bytes_per_step": venv.d2h_bytes_per_step() * world, "steps": Ke,
-             "note": "RocketVecEnv.step_host on every rank: the kernel reads the pinned host actions and writes obs|reward|done to mapped pinned host memory (the PCIe traffic overlaps the integration); "
-                     "max wall time over ranks"}
+             "api": f"RocketVecEnv.step_host_async (rlr_pipe_submit / rlr_pipe_wait, depth {D})",
+             "synchronous_step_host": e2e_sync,
+             "pcie_ceiling": {"value": pcie_ceiling, "unit": "env-steps/s", "d2h_GBps_all_ranks": d2h_gbs,
+                              "how": "the same bytes per step as plain cudaMemcpyAsync D2H + H2D on two streams, all ranks at once, no kernel"},
+             "frac_of_pcie_ceiling": e2e / pcie_ceiling,
+             "note": "every rank: pinned host actions -> H2D copy -> step kernel -> D2H copy of obs|reward|done into pinned host memory, `depth` slots in "
+                     "flight, the host reads each step's result; max wall time over ranks.  synchronous_step_host = one blocking call per step "
+                     "(mapped pinned memory written by the kernel)"}
 
     # ---- BASELINE config 4 for the record: 2^20 environments in total, sharded over the ranks by global index (2^20 / world per GPU),
     # one launch per step, back to back, device-timed, max over ranks, the statistics all-gather included
@@ -230,7 +281,7 @@ def run_ours(args):
     for t in range(K4):
         env4.step_tensor(a4[t % 8])
     if world > 1:
-        dist.all_gather_into_tensor(stat_gather, env4.stats.unsqueeze(0))
+        exchange.all_gather(env4.stats)
     c1.record()
     c1.synchronize()
     t4 = torch.tensor([c0.elapsed_time(c1)], dtype=torch.float64, device=dev)
@@ -276,8 +327,72 @@ def run_ours(args):
         e1.synchronize()
         f32_fused = n * Tr / (e0.elapsed_time(e1) * 1e-3)
         del env32
-        # ---- roofline of the dominant kernel (step_kernel<Sys6>): FP64 ALU bound, peak measured in this run
         peak = fma_peak("f64", device=dev)
+        # ---- the rest of the measurement contract, all timed like `value`: one launch per event pair, L2 read-flushed
+        # in between.  Fixed policies of test_6DOF_environment.py:19-20, BASELINE config 2 (3DOF, 4 096 envs) and config 1 (1DOF)
+        def flushed_us(batch, act_fn, steps):
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for t in range(steps):
+                if flush is not None:
+                    torch.sum(flush, dim=(0,), keepdim=True, out=flush_sink)
+                evs[t][0].record()
+                batch.step_tensor(act_fn(t))
+                evs[t][1].record()
+            torch.cuda.synchronize(dev)
+            return sum(a_.elapsed_time(b_) for a_, b_ in evs) * 1e3 / steps
+
+        Kv = min(K, 100)
+        extra = {}
+        for name, act in (("fixed_policy_null_action_[0,0,-1]", (0.0, 0.0, -1.0)), ("fixed_policy_[1,1,-0.5]", (1.0, 1.0, -0.5))):
+            envp = RocketBatch(spec, n, device=dev, seed=42, env_offset=rank * n, math_mode=args.math)
+            envp.reset()
+            a_fix = torch.tensor(act, dtype=torch.float32, device=dev).repeat(n, 1).contiguous()
+            for t in range(PREP_STEPS):
+                envp.step_tensor(a_fix)
+            envp.read_stats(reset=True)
+            us = flushed_us(envp, lambda t: a_fix, Kv)
+            sp = envp.read_stats()
+            fl_ = FLOP_STEP * sp["steps"] + FLOP_ATTEMPT * sp["attempts"]
+            extra[name] = {"env_steps_per_s": n / us * 1e6, "us_per_step": us, "attempts_per_step": sp["attempts"] / max(1, sp["steps"]),
+                           "roofline_frac": fl_ / (us * 1e-6 * Kv) / 1e12 / peak}
+            del envp
+        from rl_rocket_b200.config import env_config_1dof, env_config_3dof
+        for name, dof_, cfg_, n_, tl_ in (("config2_3dof_4096_envs", 3, env_config_3dof(), 4096, 3000), ("3dof_65536_envs", 3, env_config_3dof(), 65536, 3000),
+                                          ("config1_1dof_single_env", 1, env_config_1dof(), 1, 3000), ("1dof_4096_envs", 1, env_config_1dof(), 4096, 3000)):
+            sp_ = EnvSpec(dof_, max_episode_steps=tl_, **cfg_)
+            e_ = RocketBatch(sp_, n_, device=dev, seed=42, math_mode=args.math)
+            e_.reset()
+            a_ = torch.empty((16, n_, sp_.nact), device=dev).uniform_(-1, 1, generator=gen)
+            for t in range(PREP_STEPS):
+                e_.step_tensor(a_[t % 16])
+            e_.read_stats(reset=True)
+            us = flushed_us(e_, lambda t: a_[t % 16], Kv)
+            sp = e_.read_stats()
+            # 3DOF flop model: 250 + 590 k per env step (trig calls counted as one flop each)
+            fl_ = 250 * sp["steps"] + 590 * sp["attempts"]
+            extra[name] = {"env_steps_per_s": n_ / us * 1e6, "us_per_step": us, "attempts_per_step": sp["attempts"] / max(1, sp["steps"]),
+                           "roofline_frac": fl_ / (us * 1e-6 * Kv) / 1e12 / peak}
+            del e_
+        # BASELINE config 5: SB3-style rollout collection through RocketVecEnv.step() (numpy in / numpy out + infos), wall clock
+        for n_ in (4096, 65536):
+            v_ = RocketVecEnv(n_, dof=6, max_episode_steps=800, device=dev, math_mode=args.math, **cfg)
+            v_.reset()
+            a_np = [actions[W + t, :n_].cpu().numpy() for t in range(8)]
+            for t in range(10):
+                v_.step(a_np[t % 8])
+            Ks = 30
+            t0 = time.perf_counter()
+            for t in range(Ks):
+                v_.step(a_np[t % 8])
+            extra[f"config5_sb3_vecenv_step_{n_}_envs"] = {"env_steps_per_s": n_ * Ks / (time.perf_counter() - t0),
+                                                            "note": "step_async + step_wait: numpy actions in, numpy obs / rewards / dones + info dicts out"}
+            del v_
+        peak32 = fma_peak("f32", device=dev)
+        f32_flops_per_step = (FLOP_STEP + FLOP_ATTEMPT * st["attempts"] / max(1, st["steps"]))
+        extra["f32_state_roofline"] = {"peak_fp32_fma_tflops": peak32, "back_to_back_frac": f32_b2b * f32_flops_per_step / 1e12 / peak32,
+                                       "fused_rollout_frac": f32_fused * f32_flops_per_step / 1e12 / peak32,
+                                       "note": "same flop model (540 + 1530 k) against the FFMA peak measured by rlr_fma_peak('f32')"}
+        # ---- roofline of the dominant kernel (step_kernel<Sys6>): FP64 ALU bound, peak measured in this run
         flops = FLOP_STEP * st["steps"] + FLOP_ATTEMPT * st["attempts"]
         kern_s = sum(step_ms) * 1e-3
         achieved = flops / kern_s / 1e12
@@ -310,17 +425,34 @@ def run_ours(args):
                            "total_envs": n * world, "math_mode": args.math,
                            "l2": "256 MiB read-flush between timed steps (outside the event pairs)" if args.l2_flush else "no flush",
                            "state_prep": f"{PREP_STEPS} untimed random-action steps so episodes are desynchronised",
-                           "collective": "all_gather of the 64-byte episode-statistics record per rank (NCCL), timed" if world > 1 else None},
+                           "collective": (("all-gather of the 64-byte episode-statistics record per rank, timed: " +
+                                           ("one kernel per rank storing into the peers' buffers over NVLink (rlr_exchange_allgather)"
+                                            if exchange.peer_memory else "NCCL all_gather (peer memory could not be mapped: %s)" % exchange.error))
+                                          if world > 1 else None)},
                 "clocks": clocks, "e2e": e2e_d, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "episodes_finished": st_all["done"], "wall_ms_timed_region": wall_ms,
                 "variants": {"back_to_back_no_flush": b2b, "fused_rollout_kernel": fused, "f32_state_back_to_back": f32_b2b,
                              "f32_state_fused_rollout": f32_fused, "unit": "env-steps/s (rank 0 only)",
-                             "config4_2p20_envs_sharded_all_ranks": config4}}
+                             "config4_2p20_envs_sharded_all_ranks": config4, **extra},
+                "gather_ms": gather_ms, "steps_ms_sum": sum(step_ms)}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
+
+
+_JSON_FD = None
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else written to fd 1 during the run (NCCL's version banner,
+    library chatter) was redirected to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def main():
@@ -335,6 +467,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-seconds", type=float, default=2.0)
+    ap.add_argument("--e2e-depth", type=int, default=3)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -347,6 +480,10 @@ def main():
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
                    "--master-port", "29511"] + sys.argv
             sys.exit(subprocess.call(cmd))
+        global _JSON_FD
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)             # keep stdout clean for the JSON line (NCCL prints its version banner to fd 1)
         run_ours(args)
 
 

@@ -185,6 +185,20 @@ int rlr_pipe_submit(RlrHostPipe* pipe, int slot, const RlrParams* p, int precisi
                     size_t pack_bytes, int64_t n, int64_t env_offset, uint64_t seed, void* compute_stream);
 int rlr_pipe_wait(RlrHostPipe* pipe, int slot);
 
+/* Per-rollout exchange of the episode-statistics records (returns / done counts: RLR_NSTATS u64 per rank) between the GPUs of ONE
+ * node over NVLink peer memory -- the one exchange step of the multi-GPU path (environments shard by index; there is no data-path
+ * collective).  Each rank creates an exchange on its device, the 64-byte CUDA-IPC handles are all-gathered once by the host side
+ * (torch.distributed, any backend), and rlr_exchange_allgather then enqueues ONE single-block kernel that writes the rank's record
+ * into every peer's table, flags it, waits for the peers' flags and copies the [world][RLR_NSTATS] table to `out` (device).
+ * Every rank must call it the same number of times.  rlr_exchange_status (host-synchronising) reports a peer that never arrived. */
+typedef struct RlrExchange RlrExchange;
+int rlr_exchange_create(RlrExchange** ex, int rank, int world);
+int rlr_exchange_handle(RlrExchange* ex, unsigned char* out64);
+int rlr_exchange_connect(RlrExchange* ex, const unsigned char* handles /* [world][64] */);
+int rlr_exchange_allgather(RlrExchange* ex, const unsigned long long* local_stats, unsigned long long* out, void* stream);
+int rlr_exchange_status(RlrExchange* ex);
+int rlr_exchange_destroy(RlrExchange* ex);
+
 /* FP64 / FP32 FMA roofline calibration: launches a dependent-chain FMA kernel, returns flops issued. */
 int rlr_fma_peak(int precision, int blocks, int threads, int iters, double* sink, double* flops_out, void* stream);
 

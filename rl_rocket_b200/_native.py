@@ -50,7 +50,9 @@ class RlrStepOut(C.Structure):
 
 EXPORTS = ("rlr_abi_version", "rlr_last_error", "rlr_sizeof_params", "rlr_ndim", "rlr_nact", "rlr_nobs",
            "rlr_reset", "rlr_step", "rlr_step_range", "rlr_rollout", "rlr_fma_peak",
-           "rlr_pipe_create", "rlr_pipe_destroy", "rlr_pipe_submit", "rlr_pipe_wait")
+           "rlr_pipe_create", "rlr_pipe_destroy", "rlr_pipe_submit", "rlr_pipe_wait",
+           "rlr_exchange_create", "rlr_exchange_handle", "rlr_exchange_connect", "rlr_exchange_allgather", "rlr_exchange_status",
+           "rlr_exchange_destroy")
 
 _lib = None
 
@@ -86,6 +88,12 @@ def load():
     lib.rlr_pipe_submit.argtypes = [C.c_void_p, C.c_int, P, C.c_int, C.c_int, RlrState, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, RlrStepOut,
                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p]
     lib.rlr_pipe_wait.argtypes = [C.c_void_p, C.c_int]
+    lib.rlr_exchange_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int]
+    lib.rlr_exchange_handle.argtypes = [C.c_void_p, C.c_void_p]
+    lib.rlr_exchange_connect.argtypes = [C.c_void_p, C.c_void_p]
+    lib.rlr_exchange_allgather.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.rlr_exchange_status.argtypes = [C.c_void_p]
+    lib.rlr_exchange_destroy.argtypes = [C.c_void_p]
     lib.rlr_fma_peak.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
     _lib = lib
     return lib

@@ -18,7 +18,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 VARIANT = os.environ.get("RLR_DEFS", "").split()     # tuning builds: RLR_VARIANT=<tag> RLR_DEFS="-DRLR_REGS6=144 ..." -> librlrocket_<tag>.so
 COMMON = VARIANT + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"), "-I", HERE]
-UNITS = [("kernels_exact.cu", ["-fmad=false"]), ("kernels_fast.cu", ["-fmad=true"]), ("fma_peak.cu", []), ("abi.cu", []), ("host_pipe.cu", [])]
+UNITS = [("kernels_exact.cu", ["-fmad=false"]), ("kernels_fast.cu", ["-fmad=true"]), ("fma_peak.cu", []), ("abi.cu", []), ("host_pipe.cu", []), ("exchange.cu", [])]
 
 
 def _sources():

@@ -1,0 +1,154 @@
+// exchange.cu -- the per-rollout exchange of the episode-statistics records between the GPUs of one node, over NVLink peer
+// memory (rlr_exchange_*).  Every rank owns one small device buffer [2 parities][world][RLR_NSTATS] u64 + [world] u32 flags,
+// exported with CUDA IPC; ONE single-block kernel per rank and rollout stores the rank's 64-byte record straight into every peer's
+// buffer, publishes a flag per peer (release, system scope), waits for the peers' flags (acquire) and copies the gathered table
+// out -- no separate collective kernel, no host synchronisation.  (The NCCL all-gather of the same 64 bytes took 92 us inside a
+// 20-step rollout on two B200s, 13 % of the rollout; this takes one small launch plus one NVLink round trip.)
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "rl_rocket_b200.h"
+
+extern "C" int rlr_set_error_(int code, const char* msg);
+
+struct RlrExchange {
+    int rank = 0, world = 0, device = 0;
+    unsigned epoch = 0;
+    unsigned char* local = nullptr;                 // this rank's buffer
+    std::vector<unsigned char*> peer;               // every rank's buffer as mapped here (peer[rank] == local)
+    unsigned char** d_peer = nullptr;               // the same table on the device
+    int* d_status = nullptr;                        // device flag: 1 = a wait timed out
+    bool connected = false;
+};
+
+namespace {
+constexpr int MAXW = 16;
+__host__ __device__ inline size_t data_bytes(int world) { return (size_t)2 * world * RLR_NSTATS * sizeof(unsigned long long); }
+__host__ __device__ inline size_t buffer_bytes(int world) { return data_bytes(world) + (size_t)world * sizeof(unsigned) + 64; }
+
+int cu(cudaError_t e) {
+    if (e == cudaSuccess) return RLR_OK;
+    char buf[200];
+    snprintf(buf, sizeof(buf), "CUDA error %d: %s", (int)e, cudaGetErrorString(e));
+    return rlr_set_error_(RLR_E_CUDA, buf);
+}
+#define CU(x) do { int rc_ = cu(x); if (rc_) return rc_; } while (0)
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// one block of world * RLR_NSTATS threads (>= 32)
+__global__ void exchange_kernel(unsigned char* const* __restrict__ peer, const unsigned long long* __restrict__ local_stats,
+                                unsigned long long* __restrict__ out, int rank, int world, unsigned epoch, int* status) {
+    const int t = threadIdx.x;
+    const int par = epoch & 1;
+    if (t < world * RLR_NSTATS) {                       // my record -> slot `rank` of every rank's table (mine included)
+        const int r = t / RLR_NSTATS, s = t % RLR_NSTATS;
+        volatile unsigned long long* dst = reinterpret_cast<unsigned long long*>(peer[r]) + ((size_t)par * world + rank) * RLR_NSTATS + s;
+        *dst = local_stats[s];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (t < world) st_release_sys(reinterpret_cast<unsigned*>(peer[t] + data_bytes(world)) + rank, epoch);
+    if (t < world) {                                    // wait for rank t's record of this epoch in MY table
+        const unsigned* flag = reinterpret_cast<const unsigned*>(peer[rank] + data_bytes(world)) + t;
+        int spins = 0;
+        while (ld_acquire_sys(flag) != epoch) {
+            __nanosleep(100);
+            if (++spins > (1 << 24)) { *status = 1; break; }       // ~2 s: a peer never arrived; give up instead of hanging the GPU
+        }
+    }
+    __syncthreads();
+    if (t < world * RLR_NSTATS) {
+        const volatile unsigned long long* src = reinterpret_cast<const unsigned long long*>(peer[rank]) + (size_t)par * world * RLR_NSTATS;
+        out[t] = src[t];
+    }
+}
+}  // namespace
+
+extern "C" {
+
+int rlr_exchange_create(RlrExchange** ex, int rank, int world) {
+    if (!ex || world < 1 || world > MAXW || rank < 0 || rank >= world) return rlr_set_error_(RLR_E_INVALID, "rlr_exchange_create: bad rank / world (<= 16)");
+    RlrExchange* e = new RlrExchange();
+    e->rank = rank; e->world = world;
+    CU(cudaGetDevice(&e->device));
+    CU(cudaMalloc(&e->local, buffer_bytes(world)));
+    CU(cudaMemset(e->local, 0, buffer_bytes(world)));
+    CU(cudaMalloc(&e->d_peer, sizeof(unsigned char*) * world));
+    CU(cudaMalloc(&e->d_status, sizeof(int)));
+    CU(cudaMemset(e->d_status, 0, sizeof(int)));
+    CU(cudaDeviceSynchronize());
+    e->peer.assign(world, nullptr);
+    e->peer[rank] = e->local;
+    *ex = e;
+    return RLR_OK;
+}
+
+int rlr_exchange_handle(RlrExchange* e, unsigned char* out64) {
+    if (!e || !out64) return rlr_set_error_(RLR_E_INVALID, "rlr_exchange_handle: NULL");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, e->local));
+    static_assert(sizeof(h) == 64, "CUDA IPC handles are 64 bytes");
+    memcpy(out64, &h, 64);
+    return RLR_OK;
+}
+
+int rlr_exchange_connect(RlrExchange* e, const unsigned char* handles) {
+    if (!e || !handles) return rlr_set_error_(RLR_E_INVALID, "rlr_exchange_connect: NULL");
+    for (int r = 0; r < e->world; ++r) {
+        if (r == e->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + 64 * r, 64);
+        void* p = nullptr;
+        CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        e->peer[r] = (unsigned char*)p;
+    }
+    CU(cudaMemcpy(e->d_peer, e->peer.data(), sizeof(unsigned char*) * e->world, cudaMemcpyHostToDevice));
+    e->connected = true;
+    return RLR_OK;
+}
+
+int rlr_exchange_allgather(RlrExchange* e, const unsigned long long* local_stats, unsigned long long* out, void* stream) {
+    if (!e || !local_stats || !out) return rlr_set_error_(RLR_E_INVALID, "rlr_exchange_allgather: NULL");
+    if (!e->connected && e->world > 1) return rlr_set_error_(RLR_E_INVALID, "rlr_exchange_allgather: call rlr_exchange_connect first");
+    if (!e->connected) {          // world == 1: the table is this rank's own buffer
+        CU(cudaMemcpy(e->d_peer, e->peer.data(), sizeof(unsigned char*) * e->world, cudaMemcpyHostToDevice));
+        e->connected = true;
+    }
+    e->epoch += 1;
+    int threads = e->world * RLR_NSTATS;
+    threads = (threads + 31) / 32 * 32;
+    exchange_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(e->d_peer, local_stats, out, e->rank, e->world, e->epoch, e->d_status);
+    return cu(cudaGetLastError());
+}
+
+int rlr_exchange_status(RlrExchange* e) {          // host-synchronising: 0 = every wait so far saw its peers
+    if (!e) return rlr_set_error_(RLR_E_INVALID, "rlr_exchange_status: NULL");
+    int s = 0;
+    CU(cudaMemcpy(&s, e->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    return s ? rlr_set_error_(RLR_E_CUDA, "rlr_exchange_allgather: a peer's record did not arrive (timeout)") : RLR_OK;
+}
+
+int rlr_exchange_destroy(RlrExchange* e) {
+    if (!e) return RLR_OK;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < e->world; ++r)
+        if (r != e->rank && e->peer[r]) cudaIpcCloseMemHandle(e->peer[r]);
+    cudaFree(e->local); cudaFree(e->d_peer); cudaFree(e->d_status);
+    cudaSetDevice(prev);
+    delete e;
+    return RLR_OK;
+}
+
+}  // extern "C"

@@ -1907,6 +1907,7 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
     float ic[S::N];
     const bool finished = active && fl.done;
     if (ic_inject == nullptr) sample_ic_warp<S::N>(p, seed, env_offset + i, st.episode + 1, finished, ic);
+    RLR_PHASE(8);                       // 8: terminal-observation stores + cooperative initial-condition sampling
     if (active) {
         if (finished) finish_and_reset<S>(p, st, ic_inject, i, ic, obs);
         RLR_PHASE(6);                   // 6: auto-reset

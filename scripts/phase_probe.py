@@ -6,13 +6,13 @@ import torch
 from rl_rocket_b200 import _native as N
 from rl_rocket_b200.config import EnvSpec
 from rl_rocket_b200.engine import RocketBatch
-from tests import goldutil as G
+from rl_rocket_b200.config import env_config_6dof
 
 NAMES = ["0 loads", "1 ctx+K0+init-step", "2 RK attempts", "3 event path", "4 normalise/obs/reward", "5 output stores", "6 auto-reset",
-         "7 obs/state stores+stats"]
+         "7 obs/state stores+stats", "8 terminal obs + IC sampling"]
 lib = N.load()
 n = int(os.environ.get("QB_N", "65536"))
-spec = EnvSpec(6, max_episode_steps=800, **G.cfg6())
+spec = EnvSpec(6, max_episode_steps=800, **env_config_6dof())
 env = RocketBatch(spec, n, seed=1, math_mode="fast"); env.reset()
 a = torch.rand((250, n, 3), device="cuda") * 2 - 1
 for t in range(150): env.step_tensor(a[t])

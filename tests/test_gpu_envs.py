@@ -419,3 +419,50 @@ def test_3dof_vtarg_output_matches_oracle():
                                     O._p(obs, C.c_float), C.byref(r), None, O._p(fl, C.c_int), O._p(ref[i], C.c_double))
                 scale = np.maximum(1.0, np.abs(ref.T))
                 assert (np.abs(vt - ref.T) <= 1e-9 * scale).all(), (mm, t, np.abs(vt - ref.T).max())
+
+
+def _exchange_worker(rank, world, port, q):
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch, torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from rl_rocket_b200.distributed import StatsExchange, aggregate
+    ex = StatsExchange(torch.device("cuda", rank))
+    rows = []
+    for it in range(50):                         # many epochs: the parity double-buffering and the flags must hold up
+        local = torch.tensor([100 * rank + it, it, rank + 1, rank, 2 * rank, 0, (rank + 1) * 70, -(rank + 1) * it], dtype=torch.int64, device=f"cuda:{rank}")
+        rows.append(ex.all_gather(local).cpu().tolist())
+    ex.check()
+    q.put((rank, ex.peer_memory, ex.error, rows))
+    dist.barrier()
+    ex.close()
+    dist.destroy_process_group()
+
+
+def test_stats_exchange_single_rank_and_two_gpus():
+    """rlr_exchange_allgather: world 1 on this GPU; world 2 over NVLink peer memory when the box has two GPUs."""
+    from rl_rocket_b200.distributed import StatsExchange
+    ex = StatsExchange(torch.device("cuda:0"))
+    assert ex.peer_memory, ex.error
+    for it in range(5):
+        local = torch.arange(8, dtype=torch.int64, device="cuda") * (it + 1)
+        assert ex.all_gather(local).cpu().tolist() == [[(it + 1) * j for j in range(8)]]
+    ex.check(); ex.close()
+    if torch.cuda.device_count() < 2:
+        return
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, 29547, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=180) for _ in range(2))
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert res[0][1] and res[1][1], (res[0][2], res[1][2])          # peer memory was mapped on both ranks
+    for it in range(50):
+        want = [[100 * r + it, it, r + 1, r, 2 * r, 0, (r + 1) * 70, -(r + 1) * it] for r in range(2)]
+        assert res[0][3][it] == want and res[1][3][it] == want, it
