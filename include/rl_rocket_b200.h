@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RLR_ABI_VERSION 3
+#define RLR_ABI_VERSION 4
 #define RLR_NMAX 14          /* state components: 14 (6DOF), 7 (3DOF / 1DOF) */
 #define RLR_MAX_DISCRETE 16
 
@@ -121,7 +121,15 @@ typedef struct RlrStepOut {
     double*  vtarg;          /* [4][n] target velocity (3 components; 2 for 3DOF, third = 0) and t_go of _compute_vtarg
                                 (rocket_env.py:986-1014 / :215-247) -- what the reference appends to vtarg_history */
     unsigned long long* stats; /* [RLR_NSTATS] device accumulators, atomically added (see below) */
+    /* Compact queue of the episodes that finished in this step -- what Monitor / DummyVecEnv put into `infos` (main.py:65-70, SB3
+     * dummy_vec_env.step_wait): the step appends one record per finished environment, so the host reads `fin_count` records instead
+     * of gathering five [n]-sized arrays.  Record = RLR_FIN_HEADER + nobs doubles: [env index, episode return, episode length,
+     * TimeLimit.truncated, flags (as above), terminal_observation[nobs]].  The caller zeroes *fin_count before the step; order is
+     * arbitrary.  Both NULL = not recorded. */
+    unsigned int* fin_count;   /* device counter */
+    double*  fin_records;      /* [n][RLR_FIN_HEADER + nobs] */
 } RlrStepOut;
+#define RLR_FIN_HEADER 5
 
 /* stats slots (all u64; returns / lengths are fixed point) */
 enum {

@@ -11,7 +11,8 @@ MAX_DISCRETE = 16
 NSTATS = 8
 STAT_NAMES = ("steps", "attempts", "done", "landed", "viol", "trunc", "len_sum", "ret_sum_fx")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
+FIN_HEADER = 5
 ACT_NORMALIZED, ACT_PHYSICAL, ACT_DISCRETE = 0, 1, 2
 MATH_EXACT, MATH_FAST = 0, 1
 F64, F32 = 0, 1
@@ -45,7 +46,7 @@ class RlrState(C.Structure):
 
 class RlrStepOut(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("obs", "reward", "reward64", "done", "truncated", "terminal_obs", "fin_ret", "fin_len",
-                                           "flags", "natt", "y_pre_reset", "reward_terms", "vtarg", "stats")]
+                                           "flags", "natt", "y_pre_reset", "reward_terms", "vtarg", "stats", "fin_count", "fin_records")]
 
 
 EXPORTS = ("rlr_abi_version", "rlr_last_error", "rlr_sizeof_params", "rlr_ndim", "rlr_nact", "rlr_nobs",

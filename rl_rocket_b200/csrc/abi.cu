@@ -93,6 +93,7 @@ int rlr_step_range(const RlrParams* p, int precision, int math_mode, RlrState st
     if ((rc = check_state(st))) return rc;
     if ((rc = check_precision(p, precision, math_mode))) return rc;
     if (!actions || !out.obs || !out.done) return fail(RLR_E_INVALID, "actions, out.obs and out.done are required");
+    if ((out.fin_records == nullptr) != (out.fin_count == nullptr)) return fail(RLR_E_INVALID, "out.fin_count and out.fin_records go together");
     if (action_kind < 0 || action_kind > 2) return fail(RLR_E_INVALID, "bad action_kind");
     if (action_kind == RLR_ACT_DISCRETE && (p->dof != 3 || p->n_discrete <= 0))
         return fail(RLR_E_INVALID, "discrete actions need dof == 3 and a discrete_table");

@@ -151,32 +151,58 @@ class RocketVecEnv(_VecEnvBase):
             self._h_actions.copy_(torch.as_tensor(a.astype(np.float32).reshape(self.num_envs, -1)))
         self._pending = True
 
+    def _fin_buffers(self):
+        """Device queue of the step's finished episodes (RlrStepOut.fin_count / fin_records) + its pinned host mirror.  One D2H copy
+        of the counter and the first `head` records follows the step; only a step that finishes more episodes than that needs a
+        second copy."""
+        if self._fin_pack is None:
+            b, n = self.batch, self.num_envs
+            rec = N.FIN_HEADER + self.spec.nobs
+            head = min(n, max(64, n // 16))
+            d = torch.zeros(1 + n * rec, dtype=torch.float64, device=self.device)          # [count as u32 in word 0 | records]
+            h = torch.zeros(1 + head * rec, dtype=torch.float64).pin_memory()
+            out = b.step_out_struct(self._h_obs, self._h_rew, self._h_done)                  # obs | reward | done in mapped pinned memory
+            out.fin_count = d.data_ptr()
+            out.fin_records = d.data_ptr() + 8
+            self._fin_pack = (d, h, out, rec, head)
+        return self._fin_pack
+
     def step_wait(self):
         assert self._pending, "step_wait() without step_async()"
         self._pending = False
-        obs, rew, done = self.step_host(self._h_actions)
-        obs_np, rew_np, done_np = obs.numpy().copy(), rew.numpy().copy(), done.numpy().astype(bool)
+        b, n, no = self.batch, self.num_envs, self.spec.nobs
+        d_fin, h_fin, out, rec, head = self._fin_buffers()
+        with torch.cuda.device(self.device):
+            d_fin[:1].zero_()
+            kind = N.ACT_DISCRETE if self.discrete else N.ACT_NORMALIZED
+            if self.trace is None:
+                b.step_raw(self._h_actions.data_ptr(), out, action_kind=kind)                # the kernel reads / writes mapped host memory
+            else:                                                                            # the trace reads the batch's own outputs
+                self._d_actions.copy_(self._h_actions, non_blocking=True)
+                out_t = b._ot.__class__.from_buffer_copy(b._ot)
+                out_t.fin_count, out_t.fin_records = out.fin_count, out.fin_records
+                b.step_raw(self._d_actions.data_ptr(), out_t, action_kind=kind)
+                self.trace.record(self._d_actions)
+                self._h_pack.copy_(b.out_pack, non_blocking=True)
+            h_fin.copy_(d_fin[:h_fin.numel()], non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        obs_np, rew_np, done_np = self._h_obs.numpy().copy(), self._h_rew.numpy().copy(), self._h_done.numpy().astype(bool)
         empty = {}                    # one fresh dict per step, shared by this step's non-terminal environments only
-        infos = _LazyInfos([empty] * self.num_envs)
-        idx = np.nonzero(done_np)[0]
-        if idx.size:
-            # the finished episodes' info fields leave the device as ONE gathered float64 block (one D2H copy, one sync)
-            b, no = self.batch, self.spec.nobs
-            sel = torch.as_tensor(idx, device=self.device)
-            pack = torch.empty((idx.size, no + 4), dtype=torch.float64, device=self.device)
-            pack[:, :no] = b.terminal_obs[sel]
-            pack[:, no] = b.fin_ret[sel]
-            pack[:, no + 1] = b.fin_len[sel]
-            pack[:, no + 2] = b.truncated[sel]
-            pack[:, no + 3] = b.flags[sel]
-            h = pack.cpu().numpy()
-            term = h[:, :no].astype(np.float32)                # exact: the values were float32
+        infos = _LazyInfos([empty] * n)
+        count = int(h_fin[:1].view(torch.int32)[0])
+        if count:
+            if count > head:          # rare: more finished episodes than the head copy carries
+                recs = d_fin[1:1 + count * rec].cpu().numpy().reshape(count, rec)
+            else:
+                recs = h_fin[1:1 + count * rec].numpy().reshape(count, rec)
+            term = recs[:, N.FIN_HEADER:].astype(np.float32)       # exact: the values were float32
             now = round(time.time() - self._t_start, 6)
-            for j, i in enumerate(idx):
-                fl = int(h[j, no + 3])
-                infos[i] = {"terminal_observation": term[j], "TimeLimit.truncated": bool(h[j, no + 2]),
-                            "episode": {"r": round(float(h[j, no]), 6), "l": int(h[j, no + 1]), "t": now},
-                            "bounds_violation": bool(fl & 1), "landed": bool(fl & 2), "is_done": True}
+            for j in range(count):
+                r = recs[j]
+                fl = int(r[4])
+                infos[int(r[0])] = {"terminal_observation": term[j], "TimeLimit.truncated": bool(r[3]),
+                                    "episode": {"r": round(float(r[1]), 6), "l": int(r[2]), "t": now},
+                                    "bounds_violation": bool(fl & 1), "landed": bool(fl & 2), "is_done": True}
         return obs_np, rew_np, done_np, infos
 
     def close(self):

@@ -3,14 +3,16 @@ usage: python scripts/ncu_summary.py gpurun_out/prof_x.ncu-rep <kernel-mangled-s
 import collections, csv, io, re, subprocess, sys
 rep, ksub, warp_steps = sys.argv[1], sys.argv[2], float(sys.argv[3])
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(io.StringIO(raw))); hdr = rows[0]; d = dict(zip(hdr, rows[2]))
+rows = list(csv.reader(io.StringIO(raw))); hdr = rows[0]; d = dict(zip(hdr, rows[2])); unit = dict(zip(hdr, rows[1]))
 print(d["Kernel Name"][:60], d["Block Size"], d["Grid Size"])
 for k in ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__waves_per_multiprocessor", "launch__occupancy_limit_registers",
           "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__icc_request_hit_rate.pct",
           "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
           "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__cycles_active.avg", "sm__cycles_elapsed.max", "smsp__inst_executed.sum",
-          "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_shared_ld.sum"]:
-    print("  ", k, d.get(k))
+          "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__sass_inst_executed_op_local_ld.sum", "smsp__sass_inst_executed_op_shared_ld.sum",
+          "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_elapsed",
+          "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]:
+    print("  ", k, d.get(k), unit.get(k, ""))
 st = [(k, float(v.replace(",", ""))) for k, v in d.items() if "smsp__average_warp" in k and "issue_stalled" in k and v not in ("", "n/a")]
 for k, v in sorted(st, key=lambda x: -x[1])[:9]:
     print("     ", k.replace("smsp__average_warps_issue_stalled_", ""), v)
@@ -27,6 +29,8 @@ for line in m.group(0).split("\n"):
     m2 = re.match(r"\s+/\*([0-9a-f]{4,})\*/", line)
     if m2 and cur: off2line[int(m2.group(1), 16)] = cur
 srcl = open("/root/repo/rl_rocket_b200/csrc/rocket_kernels.cuh").read().split("\n")
+if m is None:
+    sys.exit(0)
 def func_of(line):
     for i in range(line - 1, -1, -1):
         if re.match(r"^(RLR_DEV|__device__|template|__global__|struct|int launch)", srcl[i]) and "(" in srcl[i]:
