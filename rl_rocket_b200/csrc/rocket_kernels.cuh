@@ -67,6 +67,9 @@ RLR_DEV void phase_mark(int k) {
 #ifndef RLR_PARK
 #define RLR_PARK 1
 #endif
+#ifndef RLR_OPAQUE_STORE_INDEX
+#define RLR_OPAQUE_STORE_INDEX 1
+#endif
 #ifndef RLR_WARP_TRACE
 #define RLR_WARP_TRACE 0
 #endif
@@ -1751,6 +1754,11 @@ RLR_DEV void load_state(const RlrState& gs, int64_t n, int64_t i, EnvState<S>& s
 }
 template <class S>
 RLR_DEV void store_state(const RlrState& gs, int64_t n, int64_t i, const EnvState<S>& st) {
+#if RLR_OPAQUE_STORE_INDEX
+    // the store addresses are recomputed from an index the compiler cannot identify with the one the loads used: otherwise it keeps the
+    // load-time addresses alive across the whole kernel and, at the register cap, spills them (a local-memory reload = an L2 round trip here)
+    asm volatile("" : "+l"(i));
+#endif
     double* y = (double*)gs.y + i;
 #pragma unroll
     for (int c = 0; c < S::N; ++c, y += n) *y = st.y[c];
