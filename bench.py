@@ -163,6 +163,10 @@ def run_ours(args):
     launches0 = env.launches
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K + 1)]
     barrier()
+    if world > 1:
+        # device-side rendezvous right before the timed region: the host barrier releases the ranks tens of microseconds apart, and a
+        # rank that starts early would otherwise book that skew as time spent waiting in the rollout's exchange
+        exchange.all_gather(env.stats)
     t_wall0 = time.perf_counter()
     for t in range(K):
         if flush is not None:
