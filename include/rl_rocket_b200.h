@@ -124,8 +124,9 @@ typedef struct RlrStepOut {
     /* Compact queue of the episodes that finished in this step -- what Monitor / DummyVecEnv put into `infos` (main.py:65-70, SB3
      * dummy_vec_env.step_wait): the step appends one record per finished environment, so the host reads `fin_count` records instead
      * of gathering five [n]-sized arrays.  Record = RLR_FIN_HEADER + nobs doubles: [env index, episode return, episode length,
-     * TimeLimit.truncated, flags (as above), terminal_observation[nobs]].  The caller zeroes *fin_count before the step; order is
-     * arbitrary.  Both NULL = not recorded. */
+     * TimeLimit.truncated, flags (as above), terminal_observation[nobs]].  Record j of a step goes to slot (count_before + j) mod n: the
+     * caller either zeroes *fin_count before the step or remembers the previous count; order within a step is arbitrary.
+     * Both NULL = not recorded. */
     unsigned int* fin_count;   /* device counter */
     double*  fin_records;      /* [n][RLR_FIN_HEADER + nobs] */
 } RlrStepOut;

@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(BSF) step_kernel_f32(const __grid_constant__ R
             if (out.terminal_obs) write_obs<Sys6>(p, out.terminal_obs, i, obs);
             if (out.fin_ret) out.fin_ret[i] = st.ep_ret;
             if (out.fin_len) out.fin_len[i] = st.k;
-            if (out.fin_records) append_fin_record<14>(p, out, i, st.ep_ret, st.k, fl, obs);
+            if (out.fin_records) append_fin_record<14>(p, out, n, i, st.ep_ret, st.k, fl, obs);
         }
     }
     float ic[14];

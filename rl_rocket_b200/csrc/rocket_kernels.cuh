@@ -1844,10 +1844,10 @@ RLR_DEV void accumulate_stats(unsigned long long* stats, bool active, const Step
 
 // one record of RlrStepOut.fin_records per finished episode (rare path: ~1.4 % of the lanes per step)
 template <int NS>
-RLR_DEV void append_fin_record(const RlrParams& p, const RlrStepOut& out, int64_t i, double ep_ret, int ep_len, const StepFlags& fl,
-                                               const float (&obs)[NS]) {
+RLR_DEV void append_fin_record(const RlrParams& p, const RlrStepOut& out, int64_t n, int64_t i, double ep_ret, int ep_len, const StepFlags& fl,
+                                  const float (&obs)[NS]) {
     const int no = (p.dof == 1) ? 2 : ((NS == 7 && p.obs_mode == RLR_OBS_GAUDET) ? 4 : NS);
-    const unsigned slot = atomicAdd(out.fin_count, 1u);
+    const unsigned slot = atomicAdd(out.fin_count, 1u) % (unsigned)n;      // a ring of n records: the counter need not be zeroed per step
     double* r = out.fin_records + (size_t)slot * (RLR_FIN_HEADER + no);
     r[0] = (double)i; r[1] = ep_ret; r[2] = (double)ep_len; r[3] = (double)fl.trunc;
     r[4] = (double)((fl.viol ? 1 : 0) | (fl.landed ? 2 : 0) | (fl.status == 1 ? 4 : 0) | (fl.status < 0 ? 8 : 0));
@@ -1925,14 +1925,15 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
             if (out.terminal_obs) write_obs<S>(p, out.terminal_obs, i, obs);
             if (out.fin_ret) out.fin_ret[i] = st.ep_ret;
             if (out.fin_len) out.fin_len[i] = st.k;
-            if (out.fin_records) append_fin_record<S::N>(p, out, i, st.ep_ret, st.k, fl, obs);
+            if (out.fin_records) append_fin_record<S::N>(p, out, n, i, st.ep_ret, st.k, fl, obs);
         }
     }
     // ---- auto-reset: the finished lanes' initial conditions are sampled by the whole warp (sample_ic_warp)
     float ic[S::N];
     const bool finished = active && fl.done;
+    RLR_PHASE(9);                       // 9: terminal-observation / finished-episode stores
     if (ic_inject == nullptr) sample_ic_warp<S::N>(p, seed, env_offset + i, st.episode + 1, finished, ic);
-    RLR_PHASE(8);                       // 8: terminal-observation stores + cooperative initial-condition sampling
+    RLR_PHASE(8);                       // 8: cooperative initial-condition sampling
     if (active) {
         if (finished) finish_and_reset<S>(p, st, ic_inject, i, ic, obs);
         RLR_PHASE(6);                   // 6: auto-reset

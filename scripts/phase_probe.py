@@ -9,7 +9,7 @@ from rl_rocket_b200.engine import RocketBatch
 from rl_rocket_b200.config import env_config_6dof
 
 NAMES = ["0 loads", "1 ctx+K0+init-step", "2 RK attempts", "3 event path", "4 normalise/obs/reward", "5 output stores", "6 auto-reset",
-         "7 obs/state stores+stats", "8 terminal obs + IC sampling"]
+         "7 obs/state stores+stats", "8 IC sampling (warp-cooperative)", "9 terminal obs / fin stores"]
 lib = N.load()
 n = int(os.environ.get("QB_N", "65536"))
 spec = EnvSpec(6, max_episode_steps=800, **env_config_6dof())
