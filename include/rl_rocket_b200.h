@@ -92,7 +92,8 @@ typedef struct RlrParams {
     float   discrete_thr[RLR_MAX_DISCRETE];        /* the rows' normalised throttle (row[1], an integer in the reference's table): what
                                                       RewardAnnealing sees under DiscreteActions3DOF, -xi * (row[1] + 1) in float64 */
     int32_t obs_mode;                              /* RLR_OBS_* */
-    int32_t reserved0;
+    float   min_thrust;                            /* lower bound applied to the de-normalised thrust [N] (the reference's open TODO at
+                                                      rocket_env.py:405, :980); 0 = off = the reference's behaviour */
 } RlrParams;
 
 /* Persistent per-environment state (device pointers, caller-owned). */

@@ -55,6 +55,8 @@ typedef struct {
     double max_gimbal;          /* deg2rad(20) */
     float  max_thrust;          /* 981e3 */
     int    obs_mode;            /* 0 normalised state; 1 (3DOF) GaudetStateObs, corrected (wrappers.py:51-66): see gaudet_obs3 */
+    float  min_thrust;          /* EXTENSION (no reference behaviour: the TODO at rocket_env.py:405, :980): lower bound of the
+                                   de-normalised thrust; 0 = off */
 } OrParams;
 
 /* ------------------------------------------------------------ small helpers */
@@ -387,10 +389,12 @@ static void denorm_action6(const OrParams* p, const float* a, float* u) {
     u[0] = (float)((double)a[0] * p->max_gimbal);
     u[1] = (float)((double)a[1] * p->max_gimbal);
     u[2] = ((a[2] + 1.0f) / 2.0f) * p->max_thrust;
+    if (p->min_thrust > 0.0f && !(u[2] >= p->min_thrust)) u[2] = (u[2] != u[2]) ? u[2] : p->min_thrust;   /* fmaxf, NaN passes */
 }
 static void denorm_action3(const OrParams* p, const float* a, float* u) {
     u[0] = (float)((double)a[0] * p->max_gimbal);
     u[1] = ((a[1] + 1.0f) / 2.0f) * p->max_thrust;
+    if (p->min_thrust > 0.0f && !(u[1] >= p->min_thrust)) u[1] = (u[1] != u[1]) ? u[1] : p->min_thrust;
 }
 
 /* DiscreteActions3DOF.action (wrappers.py:34): the table row is an int64 ndarray, so Rocket._denormalize_action
@@ -398,6 +402,7 @@ static void denorm_action3(const OrParams* p, const float* a, float* u) {
 static void denorm_action3_row(const OrParams* p, const float* row, float* u) {
     u[0] = (float)((double)row[0] * p->max_gimbal);
     u[1] = (float)((((double)row[1] + 1.0) / 2.0) * (double)p->max_thrust);
+    if (p->min_thrust > 0.0f && u[1] < p->min_thrust) u[1] = p->min_thrust;
 }
 
 /* ------------------------------------------------------- simulators */

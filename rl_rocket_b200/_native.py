@@ -36,7 +36,7 @@ class RlrParams(C.Structure):
         ("att_traj_c", C.c_double * 3), ("att_land_c", C.c_double * 3),
         ("max_gimbal", C.c_double), ("max_thrust", C.c_float),
         ("n_discrete", C.c_int32), ("discrete_table", C.c_float * (2 * MAX_DISCRETE)),
-        ("discrete_thr", C.c_float * MAX_DISCRETE), ("obs_mode", C.c_int32), ("reserved0", C.c_int32),
+        ("discrete_thr", C.c_float * MAX_DISCRETE), ("obs_mode", C.c_int32), ("min_thrust", C.c_float),
     ]
 
 

@@ -59,7 +59,7 @@ class EnvSpec:
     """Everything derived from the constructor kwargs: the kernel POD plus the host-side arrays."""
 
     def __init__(self, dof, IC=None, ICRange=None, timestep=None, seed=None, reward_coeff=None, trajectory_limits=None,
-                 landing_params=None, max_episode_steps=0, reward_mode=0, discrete_table=None, obs_mode=0):
+                 landing_params=None, max_episode_steps=0, reward_mode=0, discrete_table=None, obs_mode=0, min_thrust=0.0):
         if dof not in (6, 3, 1):
             raise ValueError("dof must be 6, 3 or 1")
         d = DEFAULTS_6DOF if dof == 6 else DEFAULTS_3DOF
@@ -74,6 +74,10 @@ class EnvSpec:
         self.max_episode_steps = int(max_episode_steps or 0)
         self.reward_mode = int(reward_mode)
         self.obs_mode = {0: 0, 1: 1, "state": 0, "gaudet": 1}[obs_mode]
+        # extension (no reference behaviour): lower bound of the de-normalised thrust, the reference's open TODO (rocket_env.py:405, :980)
+        self.min_thrust = float(min_thrust)
+        if not (0.0 <= self.min_thrust <= MAX_THRUST):
+            raise ValueError("min_thrust must lie in [0, max_thrust]")
         if self.obs_mode == 1 and dof != 3:
             raise ValueError("obs_mode='gaudet' (GaudetStateObs, wrappers.py:51-66) is defined for the 3DOF environment")
         self.ndim = 14 if dof == 6 else 7
@@ -139,7 +143,8 @@ class EnvSpec:
         rows = np.asarray(table)
         if rows.ndim != 2 or rows.shape[1] != 2 or not (0 < rows.shape[0] <= MAX_DISCRETE):
             raise ValueError(f"discrete table must be [n<= {MAX_DISCRETE}][2]")
-        phys = [np.float32([r[0] * self.max_gimbal, (r[1] + 1) / 2.0 * self.max_thrust]) for r in rows]
+        floor = self.min_thrust if self.min_thrust > 0 else -np.inf
+        phys = [np.float32([r[0] * self.max_gimbal, max((r[1] + 1) / 2.0 * self.max_thrust, floor)]) for r in rows]
         self.discrete_table = np.stack(phys).astype(np.float32)
         self.discrete_rows = np.array(rows, dtype=np.float32)      # the normalised rows: RewardAnnealing sees row[1] (wrappers.py:80)
         if hasattr(self, "state_normalizer"):
@@ -156,6 +161,7 @@ class EnvSpec:
         p = self.params
         p.dof, p.reward_mode, p.max_episode_steps = self.dof, self.reward_mode, self.max_episode_steps
         p.obs_mode = self.obs_mode
+        p.min_thrust = self.min_thrust
         p.dt = float(self.timestep)
         p.dt_ms = timestep_ms(self.timestep)
         rc = self.reward_coeff
@@ -197,7 +203,7 @@ class EnvSpec:
         kw = dict(dof=self.dof, IC=self.IC, ICRange=self.ICRange, timestep=self.timestep, seed=self.seed,
                   reward_coeff=self.reward_coeff, trajectory_limits=self.trajectory_limits, landing_params=self.landing_params,
                   max_episode_steps=self.max_episode_steps, reward_mode=self.reward_mode,
-                  discrete_table=None, obs_mode=self.obs_mode)
+                  discrete_table=None, obs_mode=self.obs_mode, min_thrust=self.min_thrust)
         kw.update(changes)
         spec = EnvSpec(**kw)
         if self.discrete_table is not None and "discrete_table" not in changes:

@@ -46,6 +46,7 @@ static int check_params(const RlrParams* p) {
     if (p->dt_ms <= 0 || !(p->dt > 0)) return fail(RLR_E_INVALID, "timestep must be a positive whole number of milliseconds");
     if (p->n_discrete < 0 || p->n_discrete > RLR_MAX_DISCRETE) return fail(RLR_E_INVALID, "n_discrete out of range");
     if (p->obs_mode != RLR_OBS_STATE && p->obs_mode != RLR_OBS_GAUDET) return fail(RLR_E_INVALID, "bad obs_mode");
+    if (!(p->min_thrust >= 0.0f) || p->min_thrust > p->max_thrust) return fail(RLR_E_INVALID, "min_thrust must lie in [0, max_thrust]");
     if (p->obs_mode == RLR_OBS_GAUDET && p->dof != 3) return fail(RLR_E_UNSUPPORTED, "RLR_OBS_GAUDET is defined for the 3DOF environment (wrappers.py:52)");
     return RLR_OK;
 }

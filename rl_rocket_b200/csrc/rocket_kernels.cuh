@@ -1646,6 +1646,7 @@ RLR_DEV void map_action(const RlrParams& p, const void* actions, int action_kind
             u[0] = (float)((double)a0 * p.max_gimbal);
             u[1] = (float)((double)a1 * p.max_gimbal);
             u[2] = fmul(fdiv(fadd(a2, 1.0f), 2.0f), p.max_thrust);
+            if (p.min_thrust > 0.0f) u[2] = fmaxf(u[2], p.min_thrust);      // (extension: the reference's minThrust TODO, rocket_env.py:980)
             a_thr = a2;
         } else { u[0] = a0; u[1] = a1; u[2] = a2; }
     } else {
@@ -1663,6 +1664,7 @@ RLR_DEV void map_action(const RlrParams& p, const void* actions, int action_kind
         if (action_kind == RLR_ACT_NORMALIZED) {
             u[0] = (float)((double)a0 * p.max_gimbal);
             u[1] = fmul(fdiv(fadd(a1, 1.0f), 2.0f), p.max_thrust);
+            if (p.min_thrust > 0.0f) u[1] = fmaxf(u[1], p.min_thrust);      // (extension: rocket_env.py:405)
             a_thr = a1;
         } else { u[0] = a0; u[1] = a1; }
         u[2] = 0.0f;

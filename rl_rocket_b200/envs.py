@@ -144,10 +144,10 @@ class Rocket6DOF(_SingleEnv):
     _dof = 6
 
     def __init__(self, IC=None, ICRange=None, timestep=None, seed=None, reward_coeff=None, trajectory_limits=None,
-                 landing_params=None, device="cuda:0", math_mode="exact"):
+                 landing_params=None, device="cuda:0", math_mode="exact", min_thrust=0.0):
         self.state_names = ["x", "y", "z", "vx", "vy", "vz", "q0", "q1", "q2", "q3", "omega1", "omega2", "omega3", "mass"]
         self.action_names = ["gimbal_y", "gimbal_z", "thrust"]
-        spec = EnvSpec(6, IC, ICRange, timestep, seed, reward_coeff, trajectory_limits, landing_params)
+        spec = EnvSpec(6, IC, ICRange, timestep, seed, reward_coeff, trajectory_limits, landing_params, min_thrust=min_thrust)
         self._init_common(spec, device, math_mode)
         self.position_bounds_space = spaces.Box(low=spec.pos_low, high=spec.pos_high, dtype=np.float32)
         self.attitude_traj_limit = spec.trajectory_limits["attitude_limit"]
@@ -170,6 +170,8 @@ class Rocket6DOF(_SingleEnv):
         gimbal_y = action[0] * self.max_gimbal
         gimbal_z = action[1] * self.max_gimbal
         thrust = (action[2] + 1) / 2.0 * self.max_thrust
+        if self._spec.min_thrust > 0:                             # extension: the reference's minThrust TODO (rocket_env.py:980)
+            thrust = max(thrust, self._spec.min_thrust)
         return np.float32([gimbal_y, gimbal_z, thrust])
 
     _denormalize_action = _physical_action
@@ -185,10 +187,10 @@ class Rocket(_SingleEnv):
     metadata = {"render.modes": ["human", "rgb_array"], "render_fps": 10}
     _dof = 3
 
-    def __init__(self, IC=None, ICRange=None, timestep=None, seed=None, reward_coeff=None, device="cuda:0", math_mode="exact"):
+    def __init__(self, IC=None, ICRange=None, timestep=None, seed=None, reward_coeff=None, device="cuda:0", math_mode="exact", min_thrust=0.0):
         self.state_names = ["x", "z", "theta", "vx", "vz", "omega", "mass"]
         self.action_names = ["gimbal", "thrust"]
-        spec = EnvSpec(self._dof, IC, ICRange, timestep, seed, reward_coeff)
+        spec = EnvSpec(self._dof, IC, ICRange, timestep, seed, reward_coeff, min_thrust=min_thrust)
         self._init_common(spec, device, math_mode)
         self.x_bound_right, self.x_bound_left = spec.x_bound_right, spec.x_bound_left
         self.y_bound_up, self.y_bound_down = spec.y_bound_up, spec.y_bound_down
@@ -207,6 +209,8 @@ class Rocket(_SingleEnv):
     def _physical_action(self, action):
         gimbal = action[0] * self.max_gimbal                      # rocket_env.py:395-406
         thrust = (action[1] + 1) / 2.0 * self.max_thrust
+        if self._spec.min_thrust > 0:                             # extension: rocket_env.py:405
+            thrust = max(thrust, self._spec.min_thrust)
         return np.float32([gimbal, thrust])
 
     _denormalize_action = _physical_action

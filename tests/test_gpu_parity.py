@@ -323,3 +323,27 @@ def test_3dof_65536_envs_one_step_teacher_forced(math_mode):
         worst = max(worst, _compare_with_oracle(f"3dof 65536 step {t}", spec, env, out))
         env.y.copy_(torch.as_tensor(vec.y).cuda())
     print(f"3DOF 65536 one-step [{math_mode}] worst normalised deviation {worst:.3e}")
+
+
+@pytest.mark.parametrize("math_mode", ["exact", "fast"])
+@pytest.mark.parametrize("dof", [6, 3])
+def test_min_thrust_extension_matches_the_oracle(dof, math_mode):
+    """`min_thrust` (extension: the reference's minThrust TODO, rocket_env.py:405, :980): CUDA against the C oracle, both builds."""
+    from oracle import c_oracle as O
+    EnvSpec, RocketBatch = _engine()
+    cfg, tl, na = (G.cfg6(), 800, 3) if dof == 6 else (G.cfg3(), 3000, 2)
+    N, T, floor = 2048, 40, 0.3 * 981e3
+    spec = EnvSpec(dof, max_episode_steps=tl, min_thrust=floor, **cfg)
+    p = O.make_params(dof, max_episode_steps=tl, min_thrust=floor, **cfg)
+    env = RocketBatch(spec, N, seed=8, math_mode=math_mode, debug_outputs=True)
+    vec = O.VecOracle(p, N, seed=8)
+    assert np.array_equal(env.reset().cpu().numpy(), vec.reset())
+    rng = np.random.RandomState(2)
+    for t in range(T):
+        a = rng.uniform(-1, 1, (N, na)).astype(np.float32)
+        env.step_tensor(torch.as_tensor(a).cuda())
+        _compare_with_oracle(f"min_thrust {dof}dof step {t}", spec, env, vec.step(a))
+    # the mass flow is thrust / (Isp g0) >= floor / (Isp g0): after T steps every environment has burnt at least that much
+    burnt = np.float64(cfg["IC"][-1]) + np.float64(cfg["ICRange"][-1]) / 2 - env.y[-1].cpu().numpy()
+    alive = env.k.cpu().numpy() == T
+    assert (burnt[alive] >= T * spec.timestep * floor / (360 * 9.81) * 0.999).all()

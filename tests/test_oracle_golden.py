@@ -146,3 +146,27 @@ def test_philox_known_answer():
     lo, hi = np.array(p.ic_low[:14]), np.array(p.ic_high[:14])
     assert (a >= lo).all() and (a <= hi).all()
     # 6f0a8e7e 0x6f0a8e7e... : the KAT is checked at the u32 level in tests/test_philox.py of the product side
+
+
+def test_min_thrust_extension_is_off_by_default_and_floors_the_thrust():
+    """EXTENSION (no reference behaviour to be at parity with): `min_thrust` is the reference's open TODO at rocket_env.py:405, :980
+    ("Add lower bound on thrust with self.minThrust").  Off (0) it must not change a single bit -- every golden trajectory above runs
+    with it off; on, a throttle below the floor integrates exactly like the throttle that maps onto the floor."""
+    ic = np.float32(G.cfg6()["IC"])
+    floor = 0.25 * 981e3
+    a_floor = np.float32([0.3, -0.2, -0.5])                  # (a + 1) / 2 * max_thrust == floor exactly in float32
+    assert np.float32((a_floor[2] + np.float32(1)) / np.float32(2)) * np.float32(981e3) == np.float32(floor)
+    ref = O.ScalarEnv(O.make_params(6, **G.cfg6())); ref.reset(ic)
+    on = O.ScalarEnv(O.make_params(6, min_thrust=floor, **G.cfg6())); on.reset(ic)
+    for _ in range(5):
+        ref.step(a_floor)
+        on.step(np.float32([0.3, -0.2, -0.9]))               # below the floor
+    assert np.array_equal(ref.y, on.y)
+    hi = O.ScalarEnv(O.make_params(6, min_thrust=floor, **G.cfg6())); hi.reset(ic)
+    ref2 = O.ScalarEnv(O.make_params(6, **G.cfg6())); ref2.reset(ic)
+    for _ in range(5):
+        hi.step(np.float32([0.3, -0.2, 0.4])); ref2.step(np.float32([0.3, -0.2, 0.4]))      # above the floor: untouched
+    assert np.array_equal(hi.y, ref2.y)
+    with pytest.raises(ValueError):
+        from rl_rocket_b200.config import EnvSpec
+        EnvSpec(6, min_thrust=2e6, **G.cfg6())
