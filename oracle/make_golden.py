@@ -393,6 +393,15 @@ def traj_gaudet(ns, seed=6100):
     save("traj_3dof_default_gaudet.npz", seed=seed + 1, **rollout(vec, a))
 
 
+def traj_3dof_timelimit(ns, seed=7300):
+    """3DOF TimeLimit truncation (gym.wrappers.TimeLimit over Rocket, main.py:65): 30-step limit, gentle actions, so every episode is cut."""
+    cfg = L.env_config_3dof()
+    p = O.make_params(3, max_episode_steps=30, **cfg)
+    vec = LiveVec(lambda: ns.Rocket(**cfg), 4, p, seed, 30)
+    a = np.random.RandomState(51).uniform(-0.3, 0.3, (100, 4, 2)).astype(np.float32)
+    save("traj_3dof_timelimit.npz", seed=seed, **rollout(vec, a))
+
+
 def main():
     if not L.available():
         sys.exit("live reference not present; golden files can only be generated in the dev container")
@@ -406,6 +415,7 @@ def main():
     traj_unclipped(ns)
     traj_discrete_annealing(ns)
     traj_gaudet(ns)
+    traj_3dof_timelimit(ns)
 
 
 if __name__ == "__main__":

@@ -94,6 +94,7 @@ TRAJ = {
     "traj_6dof_unclipped.npz": (6, cfg6, 800, 0, "norm"),
     "traj_3dof_unclipped.npz": (3, cfg3, 3000, 0, "norm"),
     "traj_3dof_discrete_annealing.npz": (3, cfg3, 3000, 1, "discrete"),
+    "traj_3dof_timelimit.npz": (3, cfg3, 30, 0, "norm"),
 }
 # observation mode per file (default: the normalised state): GaudetStateObs (wrappers.py:51-66) with its defects fixed, generated
 # by oracle/make_golden.py::gaudet_fixed over the live reference environment
