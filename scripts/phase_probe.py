@@ -12,7 +12,7 @@ NAMES = ["0 loads", "1 ctx+K0+init-step", "2 RK attempts", "3 event path", "4 no
          "7 obs/state stores+stats", "8 IC sampling (warp-cooperative)", "9 terminal obs / fin stores"]
 lib = N.load()
 n = int(os.environ.get("QB_N", "65536"))
-spec = EnvSpec(6, max_episode_steps=800, **env_config_6dof())
+spec = EnvSpec(6, max_episode_steps=int(os.environ.get("PP_TL", "800")), **env_config_6dof())
 env = RocketBatch(spec, n, seed=1, math_mode="fast"); env.reset()
 a = torch.rand((250, n, 3), device="cuda") * 2 - 1
 for t in range(150): env.step_tensor(a[t])
