@@ -174,7 +174,12 @@ def run_ours(args):
         ev[t][0].record()
         env.step_tensor(actions[W + t])
         ev[t][1].record()
-    # per-rollout exchange of returns / done counts (all-gather of the 8-slot statistics record), timed
+    # per-rollout exchange of returns / done counts (all-gather of the 8-slot statistics record), timed.  The ranks reach this point
+    # skewed by their (untimed, outside the event pairs) L2-flush kernels -- 20 x 40 us of memory-bound work differ by tens of microseconds
+    # between GPUs -- so one untimed exchange first absorbs that benchmarking artefact; the skew of the steps themselves stays in the
+    # result through the max over ranks of the per-rank step sums.
+    if world > 1:
+        exchange.all_gather(env.stats)
     ev[K][0].record()
     if world > 1:
         stat_gather = exchange.all_gather(env.stats)
@@ -187,8 +192,14 @@ def run_ours(args):
     clocks = sampler.stop() if rank == 0 else None
     launches = env.launches - launches0
     t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        mine = torch.tensor([sum(step_ms), gather_ms, wall_ms], dtype=torch.float64, device=dev)
+        allr = torch.zeros((world, 3), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(allr, mine.unsqueeze(0))
+        per_rank = {"steps_ms_sum": [round(v, 4) for v in allr[:, 0].tolist()], "exchange_ms": [round(v, 4) for v in allr[:, 1].tolist()],
+                    "host_wall_ms": [round(v, 3) for v in allr[:, 2].tolist()]}
     max_ms = float(t_ms.item())
     st = env.read_stats()
     if world > 1:
@@ -438,7 +449,7 @@ def run_ours(args):
                 "variants": {"back_to_back_no_flush": b2b, "fused_rollout_kernel": fused, "f32_state_back_to_back": f32_b2b,
                              "f32_state_fused_rollout": f32_fused, "unit": "env-steps/s (rank 0 only)",
                              "config4_2p20_envs_sharded_all_ranks": config4, **extra},
-                "gather_ms": gather_ms, "steps_ms_sum": sum(step_ms)}
+                "gather_ms": gather_ms, "steps_ms_sum": sum(step_ms), "per_rank": per_rank}
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

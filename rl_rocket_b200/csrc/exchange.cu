@@ -61,8 +61,8 @@ __global__ void exchange_kernel(unsigned char* const* __restrict__ peer, const u
         const unsigned* flag = reinterpret_cast<const unsigned*>(peer[rank] + data_bytes(world)) + t;
         int spins = 0;
         while (ld_acquire_sys(flag) != epoch) {
-            __nanosleep(100);
-            if (++spins > (1 << 24)) { *status = 1; break; }       // ~2 s: a peer never arrived; give up instead of hanging the GPU
+            if (++spins > 256) __nanosleep(64);                    // poll hard first (the peers are usually a few microseconds away)
+            if (spins > (1 << 24)) { *status = 1; break; }         // > 1 s: a peer never arrived; give up instead of hanging the GPU
         }
     }
     __syncthreads();
