@@ -75,18 +75,26 @@ __global__ void exchange_kernel(unsigned char* const* __restrict__ peer, const u
 
 extern "C" {
 
+int rlr_exchange_destroy(RlrExchange* e);
+
+static int exchange_init(RlrExchange* e) {
+    CU(cudaGetDevice(&e->device));
+    CU(cudaMalloc(&e->local, buffer_bytes(e->world)));
+    CU(cudaMemset(e->local, 0, buffer_bytes(e->world)));
+    CU(cudaMalloc(&e->d_peer, sizeof(unsigned char*) * e->world));
+    CU(cudaMalloc(&e->d_status, sizeof(int)));
+    CU(cudaMemset(e->d_status, 0, sizeof(int)));
+    CU(cudaDeviceSynchronize());
+    return RLR_OK;
+}
+
 int rlr_exchange_create(RlrExchange** ex, int rank, int world) {
     if (!ex || world < 1 || world > MAXW || rank < 0 || rank >= world) return rlr_set_error_(RLR_E_INVALID, "rlr_exchange_create: bad rank / world (<= 16)");
     RlrExchange* e = new RlrExchange();
     e->rank = rank; e->world = world;
-    CU(cudaGetDevice(&e->device));
-    CU(cudaMalloc(&e->local, buffer_bytes(world)));
-    CU(cudaMemset(e->local, 0, buffer_bytes(world)));
-    CU(cudaMalloc(&e->d_peer, sizeof(unsigned char*) * world));
-    CU(cudaMalloc(&e->d_status, sizeof(int)));
-    CU(cudaMemset(e->d_status, 0, sizeof(int)));
-    CU(cudaDeviceSynchronize());
     e->peer.assign(world, nullptr);
+    const int rc = exchange_init(e);
+    if (rc) { rlr_exchange_destroy(e); return rc; }
     e->peer[rank] = e->local;
     *ex = e;
     return RLR_OK;
@@ -145,7 +153,9 @@ int rlr_exchange_destroy(RlrExchange* e) {
     cudaDeviceSynchronize();
     for (int r = 0; r < e->world; ++r)
         if (r != e->rank && e->peer[r]) cudaIpcCloseMemHandle(e->peer[r]);
-    cudaFree(e->local); cudaFree(e->d_peer); cudaFree(e->d_status);
+    if (e->local) cudaFree(e->local);
+    if (e->d_peer) cudaFree(e->d_peer);
+    if (e->d_status) cudaFree(e->d_status);
     cudaSetDevice(prev);
     delete e;
     return RLR_OK;

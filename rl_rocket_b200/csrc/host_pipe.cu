@@ -31,20 +31,28 @@ static int cu(cudaError_t e) {
 
 extern "C" {
 
-int rlr_pipe_create(RlrHostPipe** pipe, int depth) {
-    if (!pipe || depth < 1 || depth > 16) return rlr_set_error_(RLR_E_INVALID, "rlr_pipe_create: need a pipe pointer and 1 <= depth <= 16");
-    RlrHostPipe* hp = new RlrHostPipe();
+int rlr_pipe_destroy(RlrHostPipe* hp);
+
+static int pipe_init(RlrHostPipe* hp, int depth) {
     hp->depth = depth;
     CU(cudaGetDevice(&hp->device));
     CU(cudaStreamCreateWithFlags(&hp->h2d, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&hp->d2h, cudaStreamNonBlocking));
-    hp->actions_ready.resize(depth); hp->kernel_done.resize(depth); hp->result_ready.resize(depth);
+    hp->actions_ready.assign(depth, nullptr); hp->kernel_done.assign(depth, nullptr); hp->result_ready.assign(depth, nullptr);
     hp->used.assign(depth, 0);
     for (int s = 0; s < depth; ++s) {
         CU(cudaEventCreateWithFlags(&hp->actions_ready[s], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&hp->kernel_done[s], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&hp->result_ready[s], cudaEventDisableTiming));
     }
+    return RLR_OK;
+}
+
+int rlr_pipe_create(RlrHostPipe** pipe, int depth) {
+    if (!pipe || depth < 1 || depth > 16) return rlr_set_error_(RLR_E_INVALID, "rlr_pipe_create: need a pipe pointer and 1 <= depth <= 16");
+    RlrHostPipe* hp = new RlrHostPipe();
+    const int rc = pipe_init(hp, depth);
+    if (rc) { rlr_pipe_destroy(hp); return rc; }      // (the error text of the failing call stays in rlr_last_error)
     *pipe = hp;
     return RLR_OK;
 }
@@ -54,8 +62,10 @@ int rlr_pipe_destroy(RlrHostPipe* hp) {
     int prev = 0;
     cudaGetDevice(&prev);
     cudaSetDevice(hp->device);
-    for (int s = 0; s < hp->depth; ++s) {
-        cudaEventDestroy(hp->actions_ready[s]); cudaEventDestroy(hp->kernel_done[s]); cudaEventDestroy(hp->result_ready[s]);
+    for (size_t s = 0; s < hp->actions_ready.size(); ++s) {
+        if (hp->actions_ready[s]) cudaEventDestroy(hp->actions_ready[s]);
+        if (hp->kernel_done[s]) cudaEventDestroy(hp->kernel_done[s]);
+        if (hp->result_ready[s]) cudaEventDestroy(hp->result_ready[s]);
     }
     if (hp->h2d) cudaStreamDestroy(hp->h2d);
     if (hp->d2h) cudaStreamDestroy(hp->d2h);
