@@ -19,9 +19,9 @@ extern "C" int rlr_debug_phases(unsigned long long* out48) {
 #endif
 
 #if RLR_WARP_TRACE
-// tuning builds only: the per-warp records of the last step launch; out = [8192][4] u64
+// tuning builds only: the per-warp records of the last step launch; out = [8192][16] u64
 extern "C" int rlr_debug_warp_trace(unsigned long long* out) {
     cudaDeviceSynchronize();
-    return (int)cudaMemcpyFromSymbol(out, rlr_fast::g_warp_trace, 8192 * 4 * 8);
+    return (int)cudaMemcpyFromSymbol(out, rlr_fast::g_warp_trace, 8192 * 16 * 8);
 }
 #endif

@@ -41,6 +41,9 @@ namespace RLR_NS {
 #ifndef RLR_PHASE_TIMING
 #define RLR_PHASE_TIMING 0
 #endif
+#ifndef RLR_WARP_TRACE
+#define RLR_WARP_TRACE 0
+#endif
 #if RLR_PHASE_TIMING
 __device__ unsigned long long g_phase_sum[16], g_phase_max[16], g_phase_cnt[16];
 RLR_DEV void phase_mark(int k) {
@@ -55,6 +58,9 @@ RLR_DEV void phase_mark(int k) {
     }
 }
 #define RLR_PHASE(k) phase_mark(k)
+#elif defined(RLR_WARP_TRACE) && RLR_WARP_TRACE
+#define RLR_PHASE(k) trace_mark(k)
+RLR_DEV void trace_mark(int k);
 #else
 #define RLR_PHASE(k)
 #endif
@@ -74,9 +80,19 @@ RLR_DEV void phase_mark(int k) {
 #define RLR_WARP_TRACE 0
 #endif
 #if RLR_WARP_TRACE
-__device__ unsigned long long g_warp_trace[8192 * 4];
+__device__ unsigned long long g_warp_trace[8192 * 16];      // per warp: sm, t0, t1, flags, then the latest arrival (ns after t0) at phase marks 0..9
 RLR_DEV unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 RLR_DEV unsigned smid_() { unsigned s; asm volatile("mov.u32 %0, %smid;" : "=r"(s)); return s; }
+RLR_DEV void trace_mark(int k) {        // the lowest active lane of whichever part of the warp passes the mark; the last part wins (max)
+    const unsigned am = __activemask();
+    const unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if ((int)(threadIdx.x & 31) == __ffs(am) - 1 && w < 8192) {
+        const unsigned long long now = globaltimer_ns();
+        if (k < 0) { g_warp_trace[w * 16 + 1] = now; for (int j = 4; j < 16; ++j) g_warp_trace[w * 16 + j] = 0ull; }
+        else atomicMax(&g_warp_trace[w * 16 + 4 + k], now - *(volatile unsigned long long*)&g_warp_trace[w * 16 + 1]);
+    }
+    __syncwarp(am);
+}
 #endif
 
 // Programmatic dependent launch (sm_90+): a step kernel lets the next kernel of the stream begin launching at once and itself waits
@@ -143,6 +159,17 @@ RLR_DEV float f32_norm4(float a, float b, float c, float d) {
 }
 // 10 * |nextafter(t, +inf) - t| for t >= 0  (rk.py:120)
 RLR_DEV double min_step_at(double t) { return 10 * fabs(__longlong_as_double(__double_as_longlong(t) + 1) - t); }
+// n / 1000.0 correctly rounded for an integer 0 <= n < 2^32 without the IEEE division: q = RN(n * RN(1/1000)), the exact residual by
+// one FMA, one correction (Markstein).  Bit-identical to the division for EVERY n < 2^32 (checked exhaustively on the host,
+// scripts/div1000_check.c).  The division's out-of-line slow path was taken by every lane with k = 0 (0 / 1000: a third of the warps
+// of a launch hold a freshly reset environment) and cost those warps ~100 serial instructions far away in the instruction cache.
+RLR_DEV double div1000_(long long n) {
+    const double a = (double)n;
+    if (n < 0 || n >= (1ll << 32)) return a / 1000.0;
+    const double q = __dmul_rn(a, 0.001);
+    const double r = __fma_rn(-q, 1000.0, a);
+    return __fma_rn(r, 0.001, q);
+}
 RLR_DEV double py_max(double a, double b) { return (b > a) ? b : a; }
 RLR_DEV double py_min(double a, double b) { return (b < a) ? b : a; }
 
@@ -692,10 +719,13 @@ struct Park6 {
     }
 };
 
-// Terminal ground event of the 6DOF solve (ivp.py:678-699): dense output Q = K^T P (rk.py:554-565, :715-737), Brent root on the
-// height polynomial, final state y(t_e).  buf = [y(14) | K6(10) | v_new(3) | dm, t_old, h, t_new]; y(t_e) is written to buf[0..13].
-// K0..K5 come from shared memory.  P[.][0] = (1,0,..,0) and P[1][.] = 0 make those terms exact no-ops, so every component needs
-// three independent 6-term FMA chains; the position rows of K are the stage velocities, recomputed from the dv rows.
+// Terminal ground event of the 6DOF solve (ivp.py:678-699): dense output Q = K^T P (rk.py:554-565, :715-737), root of the height
+// polynomial, final state y(t_e).  buf = [y(14) | K6(10) | v_new(3) | dm, t_old, h, t_new]; y(t_e) is written to buf[0..13].
+// K0..K5 come from shared memory.  P[.][0] = (1,0,..,0) and P[1][.] = 0 make those terms exact no-ops; the position rows of K are
+// the stage velocities, recomputed from the dv rows.
+#if RLR_EXACT
+// Exact build: scipy's own evaluation order -- Q = K^T P per component (three 6-term chains), then the polynomial in x, and
+// Brent's method for the root.
 __device__ __noinline__ void event_path6(const double2* __restrict__ sKt, double* __restrict__ buf) {
 #define KS(j, cc) (((cc) & 1) ? sKt[(j) * KROW + ((cc) >> 1) * BS6].y : sKt[(j) * KROW + ((cc) >> 1) * BS6].x)
     const double dm = buf[27], t = buf[28], h = buf[29], t_new = buf[30];
@@ -716,35 +746,8 @@ __device__ __noinline__ void event_path6(const double2* __restrict__ sKt, double
     const double hq0 = vx0, hq1 = DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 1),
                  hq2 = DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 2),
                  hq3 = DENSE_Q(vx0, vs[1][0], vs[2][0], vs[3][0], vs[4][0], vx6, 3);
-#if !RLR_EXACT
-    // Fast build: the root of the height quartic  g(x) = r0 + h x (q0 + x (q1 + x (q2 + x q3))),  x = (t_e - t) / h in [0, 1],  by
-    // Newton's method from the secant point (quadratic convergence: 5 steps reach the rounding floor; Brent's bisection /
-    // inverse-quadratic steps with their IEEE divisions were the longest serial chain of the launch).  Anything unexpected
-    // (non-finite, left the bracket, residual not at rounding level) falls back to brentq_event, so the result is always a
-    // root to ~4 ulp -- the same tolerance scipy's brentq (xtol = rtol = 4 eps) guarantees.
-    double xx;
-    {
-        const double g0 = buf[0];
-        const double g1 = h * (((hq0 + hq1) + hq2) + hq3) + g0;
-        double x = RLR_DIV(g0, g0 - g1);
-        double gx = 0.0;
-#pragma unroll 1
-        for (int it = 0; it < 5; ++it) {
-            const double s = fma(fma(fma(hq3, x, hq2), x, hq1), x, hq0);
-            const double ds = fma(fma(fma(4.0 * hq3, x, 3.0 * hq2), x, 2.0 * hq1), x, hq0);
-            gx = fma(h * x, s, g0);
-            x = x - RLR_DIV(gx, h * ds);
-        }
-        const double s = fma(fma(fma(hq3, x, hq2), x, hq1), x, hq0);
-        gx = fma(h * x, s, g0);
-        const double tol = 64 * 2.220446049250313e-16 * (fabs(g0) + fabs(g1));
-        if (x >= 0.0 && x <= 1.0 && fabs(gx) <= tol) xx = x;
-        else xx = RLR_DIV(brentq_event(hq0, hq1, hq2, hq3, g0, t, h, t, t_new) - t, h);
-    }
-#else
     const double root = brentq_event(hq0, hq1, hq2, hq3, buf[0], t, h, t, t_new);
     const double xx = RLR_DIV(root - t, h);
-#endif
     const double p1 = xx, p2 = p1 * xx, p3 = p2 * xx, p4 = p3 * xx;
 #define DENSE_Y(yold, k0, k2, k3, k4, k5, k6)                                                                \
     (h * ((((k0) * p1 + DENSE_Q(k0, k2, k3, k4, k5, k6, 1) * p2) + DENSE_Q(k0, k2, k3, k4, k5, k6, 2) * p3) + \
@@ -758,6 +761,98 @@ __device__ __noinline__ void event_path6(const double2* __restrict__ sKt, double
 #undef DENSE_Q
 #undef KS
 }
+#else
+// Fast build: the same dense output with the sums regrouped so that the per-component work is ONE 6-term chain instead of three:
+//   y_i(t_e) = y_i + h sum_j w_j K_j[i],   w_j = sum_c P[j][c] x^(c+1)   (x = (t_e - t) / h; w_1 = 0),
+// and for the position rows (K_j[r] = stage velocity v + h sum_l a_jl K_l[dv])
+//   r_i(t_e) = r_i + h ((sum_j w_j) v_i + h sum_l W_l K_l[dv_i]),   W_l = sum_{j > l} w_j a_jl   (row 6 of the tableau = B -> v_new),
+// so no stage velocity is rebuilt except the four height-rate values the root finder needs.  The root of the height quartic
+//   g(x) = r0 + h x (q0 + x (q1 + x (q2 + x q3)))  in [0, 1]
+// comes from Newton's method started at the secant point (quadratic convergence: at most 5 steps, stopped when the update is below
+// one ulp of x); anything unexpected (non-finite, left the bracket, residual not at rounding level) falls back to brentq_event, so
+// the result is always a root to ~4 ulp -- the tolerance scipy's brentq (xtol = rtol = 4 eps) guarantees.
+// No local-memory argument buffer (its loads were L2 round trips on the critical chain of the last warps of a launch: ground event
+// -> reward -> auto-reset): six scalars come in registers, and the results go back through the lane's own stage-matrix column, which
+// is dead once the episode has ended --
+//   row 0, pair p:  D[2p], D[2p+1]   D_c = sum_{j<=5} w_j K_j[c]  (c = dv, dq, dw components; the caller adds w_6 K6[c] from registers)
+//   row 1:          (PW_0, PW_1), (PW_2, w_6), (S, x)            PW_i = sum_l W_l K_l[dv_i],  S = sum_j w_j
+__device__ __noinline__ void event_path6(double2* sKt, double g0, double vx0, double vx6, double h, double t, double t_new) {
+#define KS2(j, p) sKt[(j) * KROW + (p) * BS6]
+    double xx;
+    {
+        // height-rate stage values 2..5 (component 0 of the dv rows) and the height polynomial (component 0 of Q = K^T P)
+        double kx[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) kx[j] = KS2(j, 0).x;
+        double vsx[6];
+#pragma unroll
+        for (int s = 2; s <= 5; ++s) {
+            double a3 = kx[0] * c_RKA[s][0];
+#pragma unroll
+            for (int j = 1; j < s; ++j) a3 = fma(kx[j], c_RKA[s][j], a3);
+            vsx[s] = fma(a3, h, vx0);
+        }
+        double hq[4];
+        hq[0] = vx0;
+#pragma unroll
+        for (int cc = 1; cc < 4; ++cc)
+            hq[cc] = ((((vx0 * c_P[0][cc] + vsx[2] * c_P[2][cc]) + vsx[3] * c_P[3][cc]) + vsx[4] * c_P[4][cc]) + vsx[5] * c_P[5][cc]) + vx6 * c_P[6][cc];
+        const double g1 = h * (((hq[0] + hq[1]) + hq[2]) + hq[3]) + g0;
+        double x = RLR_DIV(g0, g0 - g1);
+        const double d3 = 4.0 * hq[3], d2 = 3.0 * hq[2], d1 = 2.0 * hq[1];
+#pragma unroll 1
+        for (int it = 0; it < 5; ++it) {
+            const double s = fma(fma(fma(hq[3], x, hq[2]), x, hq[1]), x, hq[0]);
+            const double ds = fma(fma(fma(d3, x, d2), x, d1), x, hq[0]);
+            const double gx = fma(h * x, s, g0);
+            const double dx = RLR_DIV(gx, h * ds);
+            x = x - dx;
+            if (fabs(dx) <= 1.2e-16 * fabs(x)) break;
+        }
+        const double s = fma(fma(fma(hq[3], x, hq[2]), x, hq[1]), x, hq[0]);
+        const double gx = fma(h * x, s, g0);
+        const double tol = 64 * 2.220446049250313e-16 * (fabs(g0) + fabs(g1));
+        if (x >= 0.0 && x <= 1.0 && fabs(gx) <= tol) xx = x;
+        else xx = RLR_DIV(brentq_event(hq[0], hq[1], hq[2], hq[3], g0, t, h, t, t_new) - t, h);
+    }
+    // w_j(x), j = 0, 2..6 (row 1 of P is zero)
+    double w[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) w[j] = (j == 1) ? 0.0 : xx * fma(fma(fma(c_P[j][3], xx, c_P[j][2]), xx, c_P[j][1]), xx, c_P[j][0]);
+    const double S = ((((w[0] + w[2]) + w[3]) + w[4]) + w[5]) + w[6];
+    // positions: PW_i = sum_l W_l K_l[dv_i], the rows streamed from shared memory
+    double PW[3];
+    {
+        double W[6];
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+            double a = w[6] * c_RKA[6][l];
+#pragma unroll
+            for (int j = 5; j > l; --j) { if (j != 1) a = fma(w[j], c_RKA[j][l], a); }
+            W[l] = a;
+        }
+        PW[0] = PW[1] = PW[2] = 0.0;
+#pragma unroll
+        for (int l = 0; l < 6; ++l) {
+            const double2 a = KS2(l, 0);
+            const double b = KS2(l, 1).x;
+            PW[0] = fma(a.x, W[l], PW[0]); PW[1] = fma(a.y, W[l], PW[1]); PW[2] = fma(b, W[l], PW[2]);
+        }
+    }
+    // dv, dq, dw: one 5-term chain per component over K0, K2..K5; pair p of row 0 is dead once D of pair p is formed
+#pragma unroll
+    for (int p = 0; p < 5; ++p) {
+        const double2 k0 = KS2(0, p), k2 = KS2(2, p), k3 = KS2(3, p), k4 = KS2(4, p), k5 = KS2(5, p);
+        const double dx_ = (((k0.x * w[0] + k2.x * w[2]) + k3.x * w[3]) + k4.x * w[4]) + k5.x * w[5];
+        const double dy_ = (p == 3) ? 0.0 : (((k0.y * w[0] + k2.y * w[2]) + k3.y * w[3]) + k4.y * w[4]) + k5.y * w[5];      // d(omega_x)/dt == 0
+        KS2(0, p) = make_double2(dx_, dy_);
+    }
+    KS2(1, 0) = make_double2(PW[0], PW[1]);
+    KS2(1, 1) = make_double2(PW[2], w[6]);
+    KS2(1, 2) = make_double2(S, xx);
+#undef KS2
+}
+#endif
 
 // solve_ivp for the 6DOF system.  y = [r(3), v(3), q(4), w(3), m] in registers; the stage derivatives K0..K5 (10 doubles
 // each: dv, dq, dw -- dr is the stage velocity, dm a per-step constant) live in shared memory at
@@ -1123,6 +1218,7 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
             h_abs *= factor;
             const double g = y[0], g_new = rn[0];
             if (((g <= 0) && (g_new >= 0)) || ((g >= 0) && (g_new <= 0))) {
+#if RLR_EXACT
                 // ---- terminal ground event: rare (once per landing) -> out-of-line, arguments through a small local buffer
                 double ebuf[32];
 #pragma unroll
@@ -1136,6 +1232,26 @@ RLR_DEV int rk45_solve6(const Sys6::Ctx& c, double t0, double t_bound, double (&
                 event_path6(sKt, ebuf);
 #pragma unroll
                 for (int i = 0; i < 14; ++i) y[i] = ebuf[i];
+#else
+                // ---- terminal ground event: rare (once per landing) -> out-of-line; six scalars in, the weighted row sums come back
+                // through the lane's own stage-matrix column (see event_path6), the K6 and old-velocity terms are added here
+                RLR_PHASE(2);           // 2: RK attempts (all of them when the step ends in an event)
+                event_path6(sKt, y[0], y[3], sv[0], h, t, t_new);
+                {
+                    const double2 r10 = KS2(1, 0), r11 = KS2(1, 1), r12 = KS2(1, 2);
+                    const double w6 = r11.y, S = r12.x, xx = r12.y;
+                    const double pw[3] = {r10.x, r10.y, r11.x};
+#pragma unroll
+                    for (int i = 0; i < 3; ++i) y[i] = fma(h, fma(h, pw[i], S * y[3 + i]), y[i]);          // uses the OLD v
+#pragma unroll
+                    for (int p = 0; p < 5; ++p) {
+                        const double2 d2 = KS2(0, p);
+                        y[3 + 2 * p] = fma(h, fma(w6, kk[2 * p], d2.x), y[3 + 2 * p]);
+                        if (RLR_LIVE(2 * p + 1)) y[4 + 2 * p] = fma(h, fma(w6, kk[2 * p + 1], d2.y), y[4 + 2 * p]);
+                    }
+                    y[13] = fma(h * xx, c.dm, y[13]);                                                    // sum_j w_j = x: the mass is linear in time
+                }
+#endif
                 status = 1;
                 break;
             }
@@ -1680,7 +1796,7 @@ RLR_DEV void env_step(const RlrParams& p, EnvState<S>& st, const float (&u)[3], 
                       StepFlags& fl, double* sK) {
     typename S::Ctx c;
     S::make_ctx(c, u);
-    const double t = (double)((long long)st.k * (long long)p.dt_ms) / 1000.0;   // round(t + dt, 3)  (simulator.py:245)
+    const double t = div1000_((long long)st.k * (long long)p.dt_ms);            // round(t + dt, 3)  (simulator.py:245)
     int natt;
     int status;
     if constexpr (S::N == 14) {
@@ -1808,6 +1924,112 @@ RLR_DEV void write_obs6_warp(const RlrParams& p, float* dst, int64_t i, bool act
     __syncwarp();                                             // the columns may be reused (rollout: next step's K0) only after the reads
 }
 
+// Step kernel, 6DOF: observation store + auto-reset of the finished environments, written out COOPERATIVELY.  The reset of a finished
+// environment (Philox initial condition -> f32 quaternion normalisation -> state, |v0|, observation; rocket_env.py:665-688) used to run
+// in the finishing lane alone -- 14 values handed over with shuffles, then ~300 divergent instructions while 31 lanes wait -- and it
+// sits at the very end of the critical chain of the last warps of a launch (ground event -> reward -> reset -> stores).  Here lane b < 7 of a
+// group of eight owns components 2b, 2b+1 of one finishing lane's initial condition (its Philox block b; four groups = up to four
+// resets per pass), the two norms come from seven shuffles, and the seven lanes store the new state and observation of that environment straight to memory; the finishing lane itself stores
+// nothing.  Same counters, bits and arithmetic as sample_ic / reset_from_ic (the reset kernel and the oracle).  The fused rollout
+// keeps its state in registers across steps and stays with sample_ic_warp + finish_and_reset.
+// `stage`: see write_obs6_warp (host destinations: rows leave as coalesced 16-byte stores through the warp's idle stage-matrix columns).
+RLR_DEV void store_obs_and_reset6_warp(const RlrParams& p, const RlrState& gs, float* dst, int64_t n, int64_t i, bool active, bool finished,
+                                         int32_t next_episode, const float (&obs)[14], double* sK, bool stage, const float* ic_inject, uint64_t seed,
+                                         int64_t env) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    float* tile_dst = dst + (i - lane) * 14;                  // row of the warp's first environment
+    const bool staged = stage && __all_sync(0xffffffffu, active) && ((reinterpret_cast<uintptr_t>(tile_dst) & 15) == 0);
+    float* tile = reinterpret_cast<float*>(sK) + w * 128;     // rows are 64 threads x 16 B = 256 floats apart; a warp owns 128 of them
+    if (staged) {
+        __syncwarp();                                         // every lane is done with its stage-matrix columns
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            const int o4 = lane * 14 + 2 * k;
+            *reinterpret_cast<float2*>(tile + (o4 >> 7) * 256 + (o4 & 127)) = make_float2(obs[2 * k], obs[2 * k + 1]);
+        }
+        __syncwarp();
+    } else if (active && !finished) {
+        write_obs<Sys6>(p, dst, i, obs);
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, finished);
+    const bool pair_ok = (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
+    const int grp = lane >> 3, sub = lane & 7, lead = lane & 24;      // four groups of eight lanes: up to four resets per pass
+    while (todo) {                                            // warp-uniform
+        int src = -1;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {                         // group g takes the g-th finished lane still to do
+            const int b = todo ? __ffs(todo) - 1 : -1;
+            if (g == grp) src = b;
+            todo &= todo - 1;
+        }
+        const bool have = src >= 0;
+        const int srcc = have ? src : 0;
+        const long long env_s = __shfl_sync(0xffffffffu, (long long)env, srcc);
+        const long long i_s = __shfl_sync(0xffffffffu, (long long)i, srcc);
+        const int ep_s = __shfl_sync(0xffffffffu, next_episode, srcc);
+        const bool work = have && sub < 7;                    // lane `sub` of the group owns components 2 sub, 2 sub + 1
+        float f0 = 0.0f, f1 = 0.0f;
+        if (work) {
+            if (ic_inject != nullptr) {
+                f0 = ic_inject[i_s * 14 + 2 * sub];
+                f1 = ic_inject[i_s * 14 + 2 * sub + 1];
+            } else {
+                uint32_t c[4] = {(uint32_t)sub, (uint32_t)ep_s, (uint32_t)((uint64_t)env_s & 0xffffffffu), (uint32_t)((uint64_t)env_s >> 32)};
+                philox4x32_10(c, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+                const uint64_t b0 = ((uint64_t)c[0] << 32) | (uint64_t)c[1], b1 = ((uint64_t)c[2] << 32) | (uint64_t)c[3];
+                const double u0 = (double)(b0 >> 11) * 0x1.0p-53, u1 = (double)(b1 >> 11) * 0x1.0p-53;
+                const double lo0 = (double)p.ic_low[2 * sub], hi0 = (double)p.ic_high[2 * sub];
+                const double lo1 = (double)p.ic_low[2 * sub + 1], hi1 = (double)p.ic_high[2 * sub + 1];
+                f0 = (float)(lo0 + (hi0 - lo0) * u0);
+                f1 = (float)(lo1 + (hi1 - lo1) * u1);
+            }
+        }
+        // components within the group: lane 1 = (2, 3), lane 2 = (4, 5), lane 3 = (6, 7), lane 4 = (8, 9)
+        const float v3 = __shfl_sync(0xffffffffu, f1, lead + 1), v4 = __shfl_sync(0xffffffffu, f0, lead + 2), v5 = __shfl_sync(0xffffffffu, f1, lead + 2);
+        const float q6 = __shfl_sync(0xffffffffu, f0, lead + 3), q7 = __shfl_sync(0xffffffffu, f1, lead + 3);
+        const float q8 = __shfl_sync(0xffffffffu, f0, lead + 4), q9 = __shfl_sync(0xffffffffu, f1, lead + 4);
+        if (work) {
+            if (sub == 3 || sub == 4) {                       // quaternion normalised in f32 (rocket_env.py:673)
+                const float nq = f32_norm4(q6, q7, q8, q9);
+                f0 = fdiv(f0, nq);
+                f1 = fdiv(f1, nq);
+            }
+            double* y = (double*)gs.y + i_s;
+            y[(int64_t)(2 * sub) * n] = (double)f0;
+            y[(int64_t)(2 * sub + 1) * n] = (double)f1;
+#if RLR_EXACT
+            const float o0 = (float)((double)f0 / p.normalizer[2 * sub]), o1 = (float)((double)f1 / p.normalizer[2 * sub + 1]);
+#else
+            const float o0 = (float)((double)f0 * p.inv_normalizer[2 * sub]), o1 = (float)((double)f1 * p.inv_normalizer[2 * sub + 1]);
+#endif
+            if (staged) {
+                const int o4 = src * 14 + 2 * sub;
+                *reinterpret_cast<float2*>(tile + (o4 >> 7) * 256 + (o4 & 127)) = make_float2(o0, o1);
+            } else if (pair_ok) {
+                *reinterpret_cast<float2*>(dst + i_s * 14 + 2 * sub) = make_float2(o0, o1);
+            } else {
+                dst[i_s * 14 + 2 * sub] = o0;
+                dst[i_s * 14 + 2 * sub + 1] = o1;
+            }
+            if (sub == 0) {
+                gs.k[i_s] = 0;
+                gs.episode[i_s] = ep_s;
+                gs.v0[i_s] = f32_norm3(v3, v4, v5);           // |v| of the initial condition in f32 (vtarg, rocket_env.py:989-991)
+                gs.ep_ret[i_s] = 0.0;
+            }
+        }
+    }
+    if (staged) {
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int f = k * 32 + lane;
+            if (f < 112) reinterpret_cast<float4*>(tile_dst)[f] = *reinterpret_cast<const float4*>(tile + k * 256 + 4 * lane);
+        }
+        __syncwarp();
+    }
+}
+
 // warp reduction of the episode statistics (REDUX for the 32-bit counters, shuffles for the 64-bit fixed-point return sum);
 // lane 0 issues one atomic per non-zero slot.
 RLR_DEV unsigned long long warp_sum(unsigned long long x) {
@@ -1890,9 +2112,7 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
     float obs[S::N];
     pdl_wait_for_predecessor();
     RLR_PHASE(-1);
-#if RLR_WARP_TRACE
-    const unsigned long long trace_t0 = globaltimer_ns();
-#endif
+
     if (active) {
         load_state<S>(gs, n, i, st);
         float u[3], a_thr;
@@ -1930,19 +2150,27 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
             if (out.fin_records) append_fin_record<S::N>(p, out, n, i, st.ep_ret, st.k, fl, obs);
         }
     }
-    // ---- auto-reset: the finished lanes' initial conditions are sampled by the whole warp (sample_ic_warp)
-    float ic[S::N];
     const bool finished = active && fl.done;
     RLR_PHASE(9);                       // 9: terminal-observation / finished-episode stores
-    if (ic_inject == nullptr) sample_ic_warp<S::N>(p, seed, env_offset + i, st.episode + 1, finished, ic);
-    RLR_PHASE(8);                       // 8: cooperative initial-condition sampling
-    if (active) {
-        if (finished) finish_and_reset<S>(p, st, ic_inject, i, ic, obs);
-        RLR_PHASE(6);                   // 6: auto-reset
-        if constexpr (S::N != 14) write_obs<S>(p, out.obs, i, obs);
-        store_state<S>(gs, n, i, st);
+    if constexpr (S::N == 14) {
+        // ---- 6DOF: the finished lanes' reset (initial condition, new state, new observation) is computed and stored by the whole warp
+        if (active && !finished) store_state<S>(gs, n, i, st);
+        RLR_PHASE(6);                   // 6: state stores of the continuing environments
+        store_obs_and_reset6_warp(p, gs, out.obs, n, i, active, finished, st.episode + 1, (const float(&)[14])obs, sK, stage_obs, ic_inject, seed,
+                                  env_offset + i);
+        RLR_PHASE(8);                   // 8: observation stores + cooperative auto-reset
+    } else {
+        // ---- auto-reset: the finished lanes' initial conditions are sampled by the whole warp (sample_ic_warp)
+        float ic[S::N];
+        if (ic_inject == nullptr) sample_ic_warp<S::N>(p, seed, env_offset + i, st.episode + 1, finished, ic);
+        RLR_PHASE(8);                   // 8: cooperative initial-condition sampling
+        if (active) {
+            if (finished) finish_and_reset<S>(p, st, ic_inject, i, ic, obs);
+            RLR_PHASE(6);               // 6: auto-reset
+            write_obs<S>(p, out.obs, i, obs);
+            store_state<S>(gs, n, i, st);
+        }
     }
-    if constexpr (S::N == 14) write_obs6_warp(p, out.obs, i, active, (const float(&)[14])obs, sK, stage_obs);
     accumulate_stats(out.stats, active, fl, ep_len, ep_ret);
     RLR_PHASE(7);                       // 7: obs / state stores, statistics
 #if RLR_WARP_TRACE
@@ -1951,10 +2179,9 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
         const unsigned n_ev = __popc(__ballot_sync(0xffffffffu, fl.status == 1)), n_fin = __popc(__ballot_sync(0xffffffffu, fl.done != 0));
         const unsigned long long w = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
         if ((threadIdx.x & 31) == 0 && w < 8192) {
-            g_warp_trace[w * 4 + 0] = smid_();
-            g_warp_trace[w * 4 + 1] = trace_t0;
-            g_warp_trace[w * 4 + 2] = globaltimer_ns();
-            g_warp_trace[w * 4 + 3] = m_att | (n_ev << 8) | (n_fin << 16);
+            g_warp_trace[w * 16 + 0] = smid_();
+            g_warp_trace[w * 16 + 2] = globaltimer_ns();
+            g_warp_trace[w * 16 + 3] = m_att | (n_ev << 8) | (n_fin << 16);
         }
     }
 #endif

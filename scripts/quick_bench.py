@@ -43,6 +43,19 @@ for N in sizes:
             print(f"[{tag}] {prec} step {mode} N={N} flushed, per-launch event pairs: mean {sum(fl)/len(fl)*1e3:.1f} us  median {fl[50]*1e3:.1f} us  min {fl[0]*1e3:.1f} us", flush=True)
             env.read_stats(reset=True)
         print(f"[{tag}] {prec} step {mode} N={N}: {ms*1e3:.1f} us/step  {N/ms*1e3:.3e} env-steps/s  att/step {st['attempts']/st['steps']:.3f}  alg {flops/150/ms/1e9:.2f} Tflop/s", flush=True)
+        if os.environ.get("QB_ROTATE"):                  # R batches stepped round-robin back to back: inputs colder than L2, code warm
+            R = int(os.environ["QB_ROTATE"])
+            envs = [env] + [RocketBatch(spec, N, seed=2 + r, math_mode=mode, precision=prec) for r in range(R - 1)]
+            for e in envs[1:]:
+                e.reset()
+                for t in range(150): e.step_tensor(a[t])
+            cnt = [0]
+            def rot():
+                envs[cnt[0] % R].step_tensor(a[150 + cnt[0] % 150]); cnt[0] += 1
+            for _ in range(2 * R): rot()
+            msr = timeit(rot, 40 * R)
+            print(f"[{tag}] {prec} step {mode} N={N} rotating over {R} batches, back to back: {msr*1e3:.1f} us/step", flush=True)
+            del envs
         env.rollout(a[:20]); torch.cuda.synchronize()      # first launch: lazy module load + local-memory sizing
         ms2 = timeit(lambda: env.rollout(a[:100]), 3) / 100
         print(f"[{tag}] {prec} rollout {mode} N={N}: {ms2*1e3:.1f} us/step  {N/ms2*1e3:.3e} env-steps/s", flush=True)

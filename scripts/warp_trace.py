@@ -15,7 +15,7 @@ env = RocketBatch(spec, n, seed=1, math_mode="fast"); env.reset()
 a = torch.rand((200, n, 3), device="cuda") * 2 - 1
 flush = torch.zeros(64 * 1024 * 1024, device="cuda")
 for t in range(160): env.step_tensor(a[t])
-buf = np.zeros((8192, 4), np.uint64)
+buf = np.zeros((8192, 16), np.uint64)
 for rep in range(3):
     flush.sum(); torch.cuda.synchronize()
     env.step_tensor(a[160 + rep]); torch.cuda.synchronize()
@@ -39,5 +39,16 @@ for rep in range(3):
           (per_sm_end.mean(), per_sm_end.min(), per_sm_end.max(), per_sm_cnt.min(), per_sm_cnt.max(), len(per_sm_end)))
     late = np.argsort(e)[-8:]
     print("    latest warps (end us, dur us, att, ev, fin, sm):", [(round(e[i], 2), round(d[i], 2), int(att[i]), int(ev[i]), int(fin[i]), int(sm[i])) for i in late])
+    # per-warp arrival times (us after the warp's start) at the phase marks, in program order
+    order = [(0, "loads"), (1, "init"), (2, "RK"), (3, "event"), (4, "reward"), (5, "out-st"), (9, "fin-st"), (6, "state-st"), (8, "obs+reset"), (7, "stats")]
+    ph = w[:, 4:14] / 1e3
+    def row(sel):
+        return "  ".join(f"{nm} {ph[sel][:, k].mean():5.2f}" for k, nm in order)
+    common = (att == 2) & (ev == 0) & (fin == 0)
+    print("    marks, common warps (mean):   ", row(common))
+    print("    marks, event warps (mean):    ", row(ev > 0))
+    print("    marks, reset-only warps (mean):", row((ev == 0) & (fin > 0)))
+    for i in late:
+        print(f"    marks, late warp att {int(att[i])} ev {int(ev[i])} fin {int(fin[i])} start {s[i]:.2f}: ", "  ".join(f"{nm} {ph[i, k]:5.2f}" for k, nm in order))
     hist, edges = np.histogram(e, bins=12)
     print("    end-time histogram:", list(zip(np.round(edges[:-1], 1), hist)))
