@@ -7,8 +7,15 @@
 A "step" is one pass of the hot path over one batch: ONE rlr_step launch advancing every environment of the rank by
 one agent step (action mapping -> adaptive RK45 solve with ground event -> reward -> TimeLimit -> auto-reset).
 N = 1 runs BASELINE config 3 (6DOF `env_config`, 65 536 envs); N > 1 keeps 65 536 envs per GPU (weak scaling; envs are
-keyed by their global index, no data-path collective) and adds the per-rollout NCCL all-gather of the episode statistics
+keyed by their global index, no data-path collective) and adds the per-rollout all-gather of the episode statistics
 to the timed region.  Prints ONE JSON line on rank 0.
+
+Timing: the K timed steps run back to back inside ONE bracket of CUDA events (barrier + synchronize on both sides).  So that every
+launch finds its inputs in HBM, not in L2, the steps rotate over a RING of independent 65 536-env batches whose combined working
+set is >= 2 x the L2 capacity ("inputs larger than L2"; the ring size is in `config.l2`).  Round 1 / early round 2 timed every
+launch with its own event pair behind an L2-flush kernel; an event pair around an EMPTY kernel reads 5 - 6 us on this platform
+(scripts/launch_overhead.cu), so that figure charged ~15 % of timestamping overhead to the kernel -- it is still reported, as
+`variants.single_launch_event_pair_l2_flushed`.
 """
 import argparse
 import json
@@ -22,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ENVS_PER_GPU = 65536
+LEAD_IN = 4                 # untimed steps queued right before the timed ones (after the barrier + synchronize)
 PREP_STEPS = 150            # untimed state preparation: desynchronise episodes so resets/events occur at their steady rate
 FLOP_STEP, FLOP_ATTEMPT = 540, 1530      # algorithmic fp64 flop per 6DOF env step: 540 + 1530*k
 BYTES_STEP = 320                          # algorithmic HBM bytes per env step when state round-trips
@@ -122,16 +130,22 @@ def run_ours(args):
     K, W = args.steps, args.warmup
     cfg = env_config()
     spec = EnvSpec(6, max_episode_steps=800, **cfg)
-    env = RocketBatch(spec, n, device=dev, seed=42, env_offset=rank * n, math_mode=args.math)
+    # ring of independent batches: combined working set >= 2 x L2, so a launch never finds its state / outputs in L2 (--ring 1: one batch)
+    l2_bytes = torch.cuda.get_device_properties(dev).L2_cache_size
+    R = args.ring if args.ring > 0 else max(2, -(-2 * l2_bytes // (BYTES_STEP * n)))
+    shared_stats = torch.zeros(8, dtype=torch.int64, device=dev)
+    ring = [RocketBatch(spec, n, device=dev, seed=42 + 1000 * j, env_offset=rank * n, math_mode=args.math, stats=shared_stats) for j in range(R)]
+    env = ring[0]
     gen = torch.Generator(device=dev).manual_seed(1234 + rank)
-    env.reset()
+    for b in ring:
+        b.reset()
     chunk = torch.empty((PREP_STEPS, n, 3), device=dev)
     chunk.uniform_(-1, 1, generator=gen)
     actions = torch.empty((W + K, n, 3), device=dev)
     actions.uniform_(-1, 1, generator=gen)
     # L2 flush between timed steps: READ a 256 MiB buffer (clean lines; a write-flush would leave 126 MB of dirty lines whose
     # write-back lands inside the next timed kernel)
-    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev) if args.l2_flush else None
+    flush = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)
     flush_sink = torch.zeros(1, dtype=torch.float32, device=dev)
     stat_gather = torch.zeros((world, 8), dtype=torch.int64, device=dev) if world > 1 else None
     exchange = None
@@ -150,47 +164,41 @@ def run_ours(args):
     time.sleep(0.25)           # (every rank pauses alike: nvidia-smi needs a moment to start sampling on rank 0)
     # state preparation and warm-up run AFTER the sampler's start-up pause, so that the GPU is busy (clocks up) right before the timed region
     for t in range(PREP_STEPS):
-        env.step_tensor(chunk[t])
-    for t in range(W):
-        if flush is not None:     # the flush kernel is warmed up too (lazy module load), and keeps the host ahead of the device queue
-            torch.sum(flush, dim=(0,), keepdim=True, out=flush_sink)
-        env.step_tensor(actions[t])
+        for b in ring:
+            b.step_tensor(chunk[t])
+    for t in range(max(W, R)):
+        ring[t % R].step_tensor(actions[t % W])
     if world > 1:        # warm-up of the exchange too (first launch: module load; the NCCL fallback sets up its channels: milliseconds)
         for _ in range(3):
             exchange.all_gather(env.stats)
             dist.all_gather_into_tensor(stat_gather, env.stats.unsqueeze(0))
     env.read_stats(reset=True)
-    launches0 = env.launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K + 1)]
+    ev0, ev_mid, ev1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     barrier()
     if world > 1:
         # device-side rendezvous right before the timed region: the host barrier releases the ranks tens of microseconds apart, and a
         # rank that starts early would otherwise book that skew as time spent waiting in the rollout's exchange
         exchange.all_gather(env.stats)
     t_wall0 = time.perf_counter()
+    for t in range(LEAD_IN):              # untimed lead-in on the same stream: the timed region starts on a busy GPU, as every step of a
+        ring[(t - LEAD_IN) % R].step_tensor(actions[t % W])      # rollout but the first does (ev0's timestamp = the last lead-in step's end)
+    launches0 = sum(b.launches for b in ring)
+    ev0.record()
     for t in range(K):
-        if flush is not None:
-            torch.sum(flush, dim=(0,), keepdim=True, out=flush_sink)          # evict L2 between timed iterations (outside the event pair)
-        ev[t][0].record()
-        env.step_tensor(actions[W + t])
-        ev[t][1].record()
-    # per-rollout exchange of returns / done counts (all-gather of the 8-slot statistics record), timed.  The ranks reach this point
-    # skewed by their (untimed, outside the event pairs) L2-flush kernels -- 20 x 40 us of memory-bound work differ by tens of microseconds
-    # between GPUs -- so one untimed exchange first absorbs that benchmarking artefact; the skew of the steps themselves stays in the
-    # result through the max over ranks of the per-rank step sums.
-    if world > 1:
-        exchange.all_gather(env.stats)
-    ev[K][0].record()
+        ring[t % R].step_tensor(actions[W + t])
+    ev_mid.record()
+    # per-rollout exchange of returns / done counts (all-gather of the 8-slot statistics record), inside the timed region; the skew the
+    # ranks accumulate over their K steps is booked to it (it waits for the slowest rank)
     if world > 1:
         stat_gather = exchange.all_gather(env.stats)
-    ev[K][1].record()
+    ev1.record()
     barrier()
     wall_ms = (time.perf_counter() - t_wall0) * 1e3
-    step_ms = [a.elapsed_time(b) for a, b in ev[:K]]
-    gather_ms = ev[K][0].elapsed_time(ev[K][1]) if world > 1 else 0.0
-    dev_ms = sum(step_ms) + gather_ms
+    step_ms = [ev0.elapsed_time(ev_mid)]
+    gather_ms = ev_mid.elapsed_time(ev1) if world > 1 else 0.0
+    dev_ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
-    launches = env.launches - launches0
+    launches = sum(b.launches for b in ring) - launches0
     t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     per_rank = None
     if world > 1:
@@ -307,7 +315,18 @@ def run_ours(args):
 
     line = None
     if rank == 0:
-        # ---- back-to-back (no flush) and fused-rollout variants, device-timed, for the record
+        # ---- the round-1 method for the record: every launch behind an L2 read-flush, timed by its own event pair
+        Kf = min(K, 100)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(Kf)]
+        for rep in range(2):
+            for t in range(Kf):
+                torch.sum(flush, dim=(0,), keepdim=True, out=flush_sink)
+                evs[t][0].record()
+                env.step_tensor(actions[W + t % K])
+                evs[t][1].record()
+            torch.cuda.synchronize(dev)
+        single_flushed = n * Kf / (sum(a_.elapsed_time(b_) for a_, b_ in evs) * 1e-3)
+        # ---- back-to-back on ONE batch (state L2-resident) and fused-rollout variants, device-timed, for the record
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(dev)
         e0.record()
@@ -316,6 +335,21 @@ def run_ours(args):
         e1.record()
         e1.synchronize()
         b2b = n * K / (e0.elapsed_time(e1) * 1e-3)
+        # two independent groups of environments stepped alternately on two streams: the tail of one launch overlaps the body of the next
+        # (what the single-stream figures cannot do: griddepcontrol.wait orders consecutive launches of a stream)
+        s2 = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
+        torch.cuda.synchronize(dev)
+        e0.record()
+        for s_ in s2:
+            s_.wait_event(e0)
+        for t in range(K):
+            with torch.cuda.stream(s2[t % 2]):
+                ring[t % R].step_tensor(actions[W + t])
+        for s_ in s2:
+            torch.cuda.current_stream(dev).wait_stream(s_)
+        e1.record()
+        e1.synchronize()
+        two_streams = n * K / (e0.elapsed_time(e1) * 1e-3)
         Tr = min(K, 200)
         env.rollout(actions[W:W + 3])            # first launch of the rollout kernel (module load) outside the timing
         e0.record()
@@ -343,13 +377,13 @@ def run_ours(args):
         f32_fused = n * Tr / (e0.elapsed_time(e1) * 1e-3)
         del env32
         peak = fma_peak("f64", device=dev)
-        # ---- the rest of the measurement contract, all timed like `value`: one launch per event pair, L2 read-flushed
-        # in between.  Fixed policies of test_6DOF_environment.py:19-20, BASELINE config 2 (3DOF, 4 096 envs) and config 1 (1DOF)
+        # ---- the rest of the measurement contract.  Fixed policies of test_6DOF_environment.py:19-20: timed like `value`.
+        # BASELINE config 2 (3DOF, 4 096 envs) and config 1 (1DOF): batches far smaller than L2, so a ring cannot keep them out of it --
+        # one launch per event pair behind an L2 read-flush (the figure includes the ~5 us an event pair around an empty kernel reads)
         def flushed_us(batch, act_fn, steps):
             evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
             for t in range(steps):
-                if flush is not None:
-                    torch.sum(flush, dim=(0,), keepdim=True, out=flush_sink)
+                torch.sum(flush, dim=(0,), keepdim=True, out=flush_sink)
                 evs[t][0].record()
                 batch.step_tensor(act_fn(t))
                 evs[t][1].record()
@@ -359,18 +393,28 @@ def run_ours(args):
         Kv = min(K, 100)
         extra = {}
         for name, act in (("fixed_policy_null_action_[0,0,-1]", (0.0, 0.0, -1.0)), ("fixed_policy_[1,1,-0.5]", (1.0, 1.0, -0.5))):
-            envp = RocketBatch(spec, n, device=dev, seed=42, env_offset=rank * n, math_mode=args.math)
-            envp.reset()
+            # timed like `value`: Kv steps in one bracket over a ring of R batches
             a_fix = torch.tensor(act, dtype=torch.float32, device=dev).repeat(n, 1).contiguous()
+            shared_p = torch.zeros(8, dtype=torch.int64, device=dev)
+            ringp = [RocketBatch(spec, n, device=dev, seed=42 + 1000 * j, env_offset=rank * n, math_mode=args.math, stats=shared_p) for j in range(R)]
+            for b in ringp:
+                b.reset()
             for t in range(PREP_STEPS):
-                envp.step_tensor(a_fix)
-            envp.read_stats(reset=True)
-            us = flushed_us(envp, lambda t: a_fix, Kv)
-            sp = envp.read_stats()
+                for b in ringp:
+                    b.step_tensor(a_fix)
+            ringp[0].read_stats(reset=True)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for t in range(Kv):
+                ringp[t % R].step_tensor(a_fix)
+            e1.record()
+            e1.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / Kv
+            sp = ringp[0].read_stats()
             fl_ = FLOP_STEP * sp["steps"] + FLOP_ATTEMPT * sp["attempts"]
             extra[name] = {"env_steps_per_s": n / us * 1e6, "us_per_step": us, "attempts_per_step": sp["attempts"] / max(1, sp["steps"]),
                            "roofline_frac": fl_ / (us * 1e-6 * Kv) / 1e12 / peak}
-            del envp
+            del ringp
         from rl_rocket_b200.config import env_config_1dof, env_config_3dof
         for name, dof_, cfg_, n_, tl_ in (("config2_3dof_4096_envs", 3, env_config_3dof(), 4096, 3000), ("3dof_65536_envs", 3, env_config_3dof(), 65536, 3000),
                                           ("config1_1dof_single_env", 1, env_config_1dof(), 1, 3000), ("1dof_4096_envs", 1, env_config_1dof(), 4096, 3000)):
@@ -380,13 +424,21 @@ def run_ours(args):
             a_ = torch.empty((16, n_, sp_.nact), device=dev).uniform_(-1, 1, generator=gen)
             for t in range(PREP_STEPS):
                 e_.step_tensor(a_[t % 16])
+            us_flushed = flushed_us(e_, lambda t: a_[t % 16], Kv)
             e_.read_stats(reset=True)
-            us = flushed_us(e_, lambda t: a_[t % 16], Kv)
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for t in range(Kv):
+                e_.step_tensor(a_[t % 16])
+            e1.record()
+            e1.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / Kv
             sp = e_.read_stats()
             # 3DOF flop model: 250 + 590 k per env step (trig calls counted as one flop each)
             fl_ = 250 * sp["steps"] + 590 * sp["attempts"]
             extra[name] = {"env_steps_per_s": n_ / us * 1e6, "us_per_step": us, "attempts_per_step": sp["attempts"] / max(1, sp["steps"]),
-                           "roofline_frac": fl_ / (us * 1e-6 * Kv) / 1e12 / peak}
+                           "roofline_frac": fl_ / (us * 1e-6 * Kv) / 1e12 / peak, "us_per_step_single_launch_event_pair_l2_flushed": us_flushed,
+                           "timing": "Kv launches back to back in one event bracket (the batch is L2-resident: it is far smaller than L2)"}
             del e_
         # BASELINE config 5: SB3-style rollout collection through RocketVecEnv.step() (numpy in / numpy out + infos), wall clock
         for n_ in (4096, 65536):
@@ -408,10 +460,11 @@ def run_ours(args):
                                        "fused_rollout_frac": f32_fused * f32_flops_per_step / 1e12 / peak32,
                                        "note": "same flop model (540 + 1530 k) against the FFMA peak measured by rlr_fma_peak('f32')"}
         # ---- roofline of the dominant kernel (step_kernel<Sys6>): FP64 ALU bound, peak measured in this run
-        flops = FLOP_STEP * st["steps"] + FLOP_ATTEMPT * st["attempts"]
+        # (the statistics record also counted the untimed lead-in steps: scale to the n * K timed env steps)
+        flops = (FLOP_STEP * st["steps"] + FLOP_ATTEMPT * st["attempts"]) * (n * K / max(1, st["steps"]))
         kern_s = sum(step_ms) * 1e-3
         achieved = flops / kern_s / 1e12
-        hbm_gbs = BYTES_STEP * st["steps"] / kern_s / 1e9
+        hbm_gbs = BYTES_STEP * n * K / kern_s / 1e9
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
@@ -438,7 +491,10 @@ def run_ours(args):
                 "config": {"workload": "BASELINE config 3: 6DOF env_config (configuration_file.py:4-34), %d envs per GPU, random U(-1,1) "
                            "f32 actions, TimeLimit 800, auto-reset, one rlr_step launch per step" % n, "envs_per_gpu": n,
                            "total_envs": n * world, "math_mode": args.math,
-                           "l2": "256 MiB read-flush between timed steps (outside the event pairs)" if args.l2_flush else "no flush",
+                           "l2": ("inputs larger than L2: the K timed steps rotate over a ring of %d independent %d-env batches (%.0f MB of state + outputs "
+                                  "touched per pass over the ring vs %.0f MB of L2), back to back inside ONE event bracket" % (R, n, R * BYTES_STEP * n / 1e6, l2_bytes / 1e6))
+                                 if R > 1 else "one batch, back to back (state L2-resident)",
+                           "ring_batches": R,
                            "state_prep": f"{PREP_STEPS} untimed random-action steps so episodes are desynchronised",
                            "collective": (("all-gather of the 64-byte episode-statistics record per rank, timed: " +
                                            ("one kernel per rank storing into the peers' buffers over NVLink (rlr_exchange_allgather)"
@@ -446,7 +502,7 @@ def run_ours(args):
                                           if world > 1 else None)},
                 "clocks": clocks, "e2e": e2e_d, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "episodes_finished": st_all["done"], "wall_ms_timed_region": wall_ms,
-                "variants": {"back_to_back_no_flush": b2b, "fused_rollout_kernel": fused, "f32_state_back_to_back": f32_b2b,
+                "variants": {"single_launch_event_pair_l2_flushed": single_flushed, "back_to_back_one_batch_l2_warm": b2b, "ring_on_two_streams_alternating": two_streams, "fused_rollout_kernel": fused, "f32_state_back_to_back": f32_b2b,
                              "f32_state_fused_rollout": f32_fused, "unit": "env-steps/s (rank 0 only)",
                              "config4_2p20_envs_sharded_all_ranks": config4, **extra},
                 "gather_ms": gather_ms, "steps_ms_sum": sum(step_ms), "per_rank": per_rank}
@@ -478,7 +534,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--math", default="fast", choices=["fast", "exact"])
-    ap.add_argument("--no-l2-flush", dest="l2_flush", action="store_false")
+    ap.add_argument("--ring", type=int, default=0, help="independent batches the timed steps rotate over (0: enough for 2 x L2; 1: one batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-seconds", type=float, default=2.0)

@@ -80,7 +80,7 @@ RLR_DEV void trace_mark(int k);
 #define RLR_WARP_TRACE 0
 #endif
 #if RLR_WARP_TRACE
-__device__ unsigned long long g_warp_trace[8192 * 16];      // per warp: sm, t0, t1, flags, then the latest arrival (ns after t0) at phase marks 0..9
+__device__ unsigned long long g_warp_trace[8192 * 16];      // per warp: sm, t0, t1, flags, then the (last) arrival time at phase marks 0..9
 RLR_DEV unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 RLR_DEV unsigned smid_() { unsigned s; asm volatile("mov.u32 %0, %smid;" : "=r"(s)); return s; }
 RLR_DEV void trace_mark(int k) {        // the lowest active lane of whichever part of the warp passes the mark; the last part wins (max)
@@ -89,9 +89,8 @@ RLR_DEV void trace_mark(int k) {        // the lowest active lane of whichever p
     if ((int)(threadIdx.x & 31) == __ffs(am) - 1 && w < 8192) {
         const unsigned long long now = globaltimer_ns();
         if (k < 0) { g_warp_trace[w * 16 + 1] = now; for (int j = 4; j < 16; ++j) g_warp_trace[w * 16 + j] = 0ull; }
-        else atomicMax(&g_warp_trace[w * 16 + 4 + k], now - *(volatile unsigned long long*)&g_warp_trace[w * 16 + 1]);
+        else *(volatile unsigned long long*)&g_warp_trace[w * 16 + 4 + k] = now;      // absolute; the host subtracts the warp's start
     }
-    __syncwarp(am);
 }
 #endif
 
@@ -1948,11 +1947,12 @@ RLR_DEV void store_obs_and_reset6_warp(const RlrParams& p, const RlrState& gs, f
             *reinterpret_cast<float2*>(tile + (o4 >> 7) * 256 + (o4 & 127)) = make_float2(obs[2 * k], obs[2 * k + 1]);
         }
         __syncwarp();
-    } else if (active && !finished) {
+    }
+    const bool pair_ok = (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
+    if (!staged && active && !finished) {
         write_obs<Sys6>(p, dst, i, obs);
     }
     unsigned todo = __ballot_sync(0xffffffffu, finished);
-    const bool pair_ok = (reinterpret_cast<uintptr_t>(dst) & 7) == 0;
     const int grp = lane >> 3, sub = lane & 7, lead = lane & 24;      // four groups of eight lanes: up to four resets per pass
     while (todo) {                                            // warp-uniform
         int src = -1;

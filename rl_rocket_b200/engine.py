@@ -18,7 +18,7 @@ def _ptr(t):
 
 class RocketBatch:
     def __init__(self, spec: EnvSpec, num_envs: int, device="cuda:0", seed=None, env_offset=0, math_mode="fast", debug_outputs=False,
-                 precision="f64"):
+                 precision="f64", stats=None):
         self.lib = N.load()                      # raises if the CUDA extension is not built
         if not torch.cuda.is_available():
             raise RuntimeError("rl_rocket_b200 needs a CUDA device (there is no CPU fallback)")
@@ -51,7 +51,10 @@ class RocketBatch:
         self.fin_ret = torch.zeros(n, dtype=torch.float64, device=dev)
         self.fin_len = torch.zeros(n, dtype=torch.int32, device=dev)
         self.flags = torch.zeros(n, dtype=torch.uint8, device=dev)
-        self.stats = torch.zeros(N.NSTATS, dtype=torch.int64, device=dev)
+        # episode statistics record; several batches of one rank (groups of environments stepped alternately) may share one
+        if stats is not None and (stats.dtype != torch.int64 or stats.numel() != N.NSTATS or not stats.is_cuda or not stats.is_contiguous()):
+            raise ValueError(f"stats must be a contiguous CUDA int64[{N.NSTATS}] tensor on the batch's device")
+        self.stats = torch.zeros(N.NSTATS, dtype=torch.int64, device=dev) if stats is None else stats
         self.debug = bool(debug_outputs)
         self.natt = torch.zeros(n, dtype=torch.int32, device=dev) if self.debug else None
         self.y_pre_reset = torch.zeros((nd, n), dtype=ydt, device=dev) if self.debug else None

@@ -41,11 +41,12 @@ for rep in range(3):
     print("    latest warps (end us, dur us, att, ev, fin, sm):", [(round(e[i], 2), round(d[i], 2), int(att[i]), int(ev[i]), int(fin[i]), int(sm[i])) for i in late])
     # per-warp arrival times (us after the warp's start) at the phase marks, in program order
     order = [(0, "loads"), (1, "init"), (2, "RK"), (3, "event"), (4, "reward"), (5, "out-st"), (9, "fin-st"), (6, "state-st"), (8, "obs+reset"), (7, "stats")]
-    ph = w[:, 4:14] / 1e3
+    ph = (w[:, 4:14] - t0[:, None]) / 1e3
     def row(sel):
         return "  ".join(f"{nm} {ph[sel][:, k].mean():5.2f}" for k, nm in order)
     common = (att == 2) & (ev == 0) & (fin == 0)
     print("    marks, common warps (mean):   ", row(common))
+    print("    marks, 3-attempt, no event/reset:", row((att == 3) & (ev == 0) & (fin == 0)))
     print("    marks, event warps (mean):    ", row(ev > 0))
     print("    marks, reset-only warps (mean):", row((ev == 0) & (fin > 0)))
     for i in late:
