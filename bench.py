@@ -33,7 +33,7 @@ LEAD_IN = 4                 # untimed steps queued right before the timed ones (
 PREP_STEPS = 150            # untimed state preparation: desynchronise episodes so resets/events occur at their steady rate
 FLOP_STEP, FLOP_ATTEMPT = 540, 1530      # algorithmic fp64 flop per 6DOF env step: 540 + 1530*k
 BYTES_STEP = 320                          # algorithmic HBM bytes per env step when state round-trips
-TRAFFIC_BYTES_PER_LAUNCH = 22.2e6         # measured DRAM read+write of one step_kernel<Sys6> launch at 65 536 envs (profiles/r01e)
+TRAFFIC_BYTES_PER_LAUNCH = 21.95e6        # measured DRAM read + write per step_kernel<Sys6> launch at 65 536 envs, in the ring (profiles/r02g)
 
 
 def env_config():
@@ -472,8 +472,9 @@ def run_ours(args):
             hbm_peak = 6650.0
         roofline = {"bound": "fp64_alu", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "traffic": TRAFFIC_BYTES_PER_LAUNCH if n == ENVS_PER_GPU else None,
-                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one step_kernel<Sys6> launch, ncu --set full "
-                                      "(profiles/r01e_step_kernel_ncu.txt); algorithmic bytes per launch = 320 B x 65536 = 21.0 MB",
+                    "traffic_source": "dram__bytes_read.sum (9.45 MB) + dram__bytes_write.sum (12.5 MB), mean of 39 consecutive step_kernel<Sys6> "
+                                      "launches of the 13-batch ring, ncu --cache-control none, one pass (profiles/r02g_ring_dram_per_launch.csv); "
+                                      "algorithmic bytes per launch = 320 B x 65536 = 21.0 MB",
                     "kernel": "step_kernel<Sys6>", "peak_source": "rlr_fma_peak DFMA microbench in this run "
                     "(MEASURED_PEAKS.json has no FP64 figure)", "flop_model": "540 + 1530*attempts per env step; attempts counted by the kernel",
                     "attempts_per_step": st["attempts"] / max(1, st["steps"]),
