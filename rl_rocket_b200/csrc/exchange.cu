@@ -49,6 +49,10 @@ __global__ void exchange_kernel(unsigned char* const* __restrict__ peer, const u
                                 unsigned long long* __restrict__ out, int rank, int world, unsigned epoch, int* status) {
     const int t = threadIdx.x;
     const int par = epoch & 1;
+    // launched with the programmatic-stream-serialization attribute: the block is placed while the rollout's last step kernel is still
+    // running (it needs no shared memory and few registers) and waits here for that kernel's completion -- the launch latency of this
+    // small kernel is off the rollout's critical path
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (t < world * RLR_NSTATS) {                       // my record -> slot `rank` of every rank's table (mine included)
         const int r = t / RLR_NSTATS, s = t % RLR_NSTATS;
         volatile unsigned long long* dst = reinterpret_cast<unsigned long long*>(peer[r]) + ((size_t)par * world + rank) * RLR_NSTATS + s;
@@ -134,7 +138,17 @@ int rlr_exchange_allgather(RlrExchange* e, const unsigned long long* local_stats
     e->epoch += 1;
     int threads = e->world * RLR_NSTATS;
     threads = (threads + 31) / 32 * 32;
-    exchange_kernel<<<1, threads, 0, (cudaStream_t)stream>>>(e->d_peer, local_stats, out, e->rank, e->world, e->epoch, e->d_status);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(1);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, exchange_kernel, (unsigned char* const*)e->d_peer, local_stats, out, e->rank, e->world, e->epoch, e->d_status));
     return cu(cudaGetLastError());
 }
 

@@ -21,7 +21,7 @@ fi
 cap() {   # name, kernel regex, skip
     ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:$2" -s $3 -c 1 -f -o $O/${TAG}_$1 $B > $O/${TAG}_ncu_$1.log 2>&1; echo "ncu $1 exit $?"
 }
-cap step "step_kernel<rlr_fast::Sys6>" 165
+cap step "step_kernel<rlr_fast::Sys6>" 1965
 cap rollout "rollout_kernel<rlr_fast::Sys6>" 1
 cap step3 "step_kernel<rlr_fast::Sys3>" 160
 cap step3dense "step_kernel<rlr_fast::Sys3Dense>" 160

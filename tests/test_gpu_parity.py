@@ -347,3 +347,30 @@ def test_min_thrust_extension_matches_the_oracle(dof, math_mode):
     burnt = np.float64(cfg["IC"][-1]) + np.float64(cfg["ICRange"][-1]) / 2 - env.y[-1].cpu().numpy()
     alive = env.k.cpu().numpy() == T
     assert (burnt[alive] >= T * spec.timestep * floor / (360 * 9.81) * 0.999).all()
+
+
+@pytest.mark.parametrize("math_mode", ["exact", "fast"])
+def test_cooperative_auto_reset_equals_the_reset_kernel(math_mode):
+    """The step kernel's auto-reset (computed and stored cooperatively by the warp: lane b of a group of eight owns components 2b, 2b+1
+    of a finished environment's initial condition) against the reset kernel (one thread per environment, scalar sampler): with
+    TimeLimit 1 every environment finishes at every step -- 32 resets per warp, eight passes of four -- and must restart bit-identical
+    to an explicit reset of the same episode index.  1000 environments: the last warp is partial."""
+    EnvSpec, RocketBatch = _engine()
+    N = 1000
+    a = torch.rand((N, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(3)) * 2 - 1
+    A = RocketBatch(EnvSpec(6, max_episode_steps=1, **G.cfg6()), N, seed=7, math_mode=math_mode)
+    B = RocketBatch(EnvSpec(6, max_episode_steps=800, **G.cfg6()), N, seed=7, math_mode=math_mode)
+    assert torch.equal(A.reset(), B.reset())
+    for t in range(3):
+        obs, rew, done = A.step_tensor(a)
+        assert bool(done.all()) and bool(A.truncated.bool().logical_or(A.flags.bool()).all())
+        obs_b = B.reset()                      # the reset kernel, next episode index
+        assert torch.equal(A.y, B.y) and torch.equal(A.v0, B.v0) and torch.equal(A.episode, B.episode)
+        assert int(A.k.abs().max()) == 0 and float(A.ep_ret.abs().max()) == 0.0
+        assert torch.equal(obs, obs_b)
+    # injected initial conditions take the same cooperative path
+    ic = torch.as_tensor(np.tile(np.float32(G.cfg6()["IC"]), (N, 1)) + np.random.RandomState(1).uniform(-0.05, 0.05, (N, 14)).astype(np.float32))
+    obs, rew, done = A.step_tensor(a, ic_inject=ic)
+    C = RocketBatch(EnvSpec(6, max_episode_steps=800, **G.cfg6()), N, seed=7, math_mode=math_mode)
+    obs_c = C.reset(ic=ic)
+    assert torch.equal(A.y, C.y) and torch.equal(A.v0, C.v0) and torch.equal(obs, obs_c)
