@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RLR_ABI_VERSION 4
+#define RLR_ABI_VERSION 5
 #define RLR_NMAX 14          /* state components: 14 (6DOF), 7 (3DOF / 1DOF) */
 #define RLR_MAX_DISCRETE 16
 
@@ -94,6 +94,10 @@ typedef struct RlrParams {
     int32_t obs_mode;                              /* RLR_OBS_* */
     float   min_thrust;                            /* lower bound applied to the de-normalised thrust [N] (the reference's open TODO at
                                                       rocket_env.py:405, :980); 0 = off = the reference's behaviour */
+    int32_t aero_mode;                             /* 3DOF / 1DOF: 0 = the reference's behaviour (alfa = 0, simulator.py:103); 1 = the
+                                                      angle-of-attack line the reference keeps commented out (simulator.py:104) enabled
+                                                      -- alfa = wrap_(-pi,pi](phi - atan2(vz, vx)), Cn = Cnalfa alfa, N = Cn Q Sref, and the
+                                                      N terms of the reference's own ax / ay / dom (simulator.py:107-127) */
 } RlrParams;
 
 /* Persistent per-environment state (device pointers, caller-owned). */

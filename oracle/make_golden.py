@@ -393,6 +393,53 @@ def traj_gaudet(ns, seed=6100):
     save("traj_3dof_default_gaudet.npz", seed=seed + 1, **rollout(vec, a))
 
 
+def aero_fixed(ns):
+    """Simulator3DOF with the angle-of-attack line of its RHS enabled (EXTENSION N4; OrParams.aero_mode = 1).  The reference keeps
+    `alfa = self._computeAoA(y)` commented out (simulator.py:103-104) and the call could not run as written: it passes the height
+    instead of the state, and `_computeAoA` ends in `self._normalize`, which does not exist (simulator.py:132-148).  This subclass
+    compiles the reference's OWN RHS source with that one line enabled and the state passed, and supplies the missing `_normalize` as
+    the wrap to (-pi, pi] built on the class's `_wrapTo2Pi`; everything downstream (Cn, N, the N terms of ax / ay / dom) is the
+    reference's code."""
+    import inspect
+    import textwrap
+    import my_environment.utils.simulator as simmod
+    src = textwrap.dedent(inspect.getsource(ns.Simulator3DOF.RHS))
+    off, on = "alfa = 0\n", "alfa = self._computeAoA(state)\n"
+    assert src.count(off) == 1 and "#alfa = self._computeAoA(y)" in src, "the reference's RHS is not the one this hook was written against"
+    scope = dict(vars(simmod))
+    exec(compile(src.replace(off, on), "<Simulator3DOF.RHS with the angle-of-attack line enabled>", "exec"), scope)
+
+    class Simulator3DOFAero(ns.Simulator3DOF):
+        RHS = scope["RHS"]
+
+        def _normalize(self, angle):
+            a = self._wrapTo2Pi(angle)
+            return a - 2. * np.pi if a > np.pi else a
+    return Simulator3DOFAero
+
+
+def traj_3dof_aero(ns, seed=8100):
+    """3DOF trajectories with the angle-of-attack normal force on: the live Rocket env with its simulator class swapped for aero_fixed."""
+    import my_environment.envs.rocket_env as envmod
+    orig = envmod.Simulator3DOF
+    envmod.Simulator3DOF = aero_fixed(ns)
+    try:
+        cfg = L.env_config_3dof()
+        p = O.make_params(3, max_episode_steps=3000, aero_mode=1, **cfg)
+        vec = LiveVec(lambda: ns.Rocket(**cfg), 4, p, seed, 3000)
+        a = np.random.RandomState(61).uniform(-1, 1, (400, 4, 2)).astype(np.float32)
+        save("traj_3dof_aero.npz", seed=seed, **rollout(vec, a))
+        # low-altitude default-constructor env: touchdowns (ground events) and resets under the aerodynamic torque
+        dcfg = dict(IC=[100, 500, np.pi / 2, -10, -50, 0, 50e3], ICRange=[10, 50, 0.1, 1, 10, 0.1, 1e3], timestep=0.1, seed=42,
+                    reward_coeff={"alfa": -0.01, "beta": -1e-8, "eta": 2, "gamma": -10, "delta": -5, "kappa": 10, "waypoint": 50, "landing_radius": 30})
+        pd_ = O.make_params(3, max_episode_steps=2000, aero_mode=1, **dcfg)
+        vec = LiveVec(lambda: ns.Rocket(**dcfg), 4, pd_, seed + 1, 2000)
+        a = np.random.RandomState(62).uniform(-1, 1, (200, 4, 2)).astype(np.float32)
+        save("traj_3dof_default_aero.npz", seed=seed + 1, **rollout(vec, a))
+    finally:
+        envmod.Simulator3DOF = orig
+
+
 def traj_3dof_timelimit(ns, seed=7300):
     """3DOF TimeLimit truncation (gym.wrappers.TimeLimit over Rocket, main.py:65): 30-step limit, gentle actions, so every episode is cut."""
     cfg = L.env_config_3dof()
@@ -416,6 +463,7 @@ def main():
     traj_discrete_annealing(ns)
     traj_gaudet(ns)
     traj_3dof_timelimit(ns)
+    traj_3dof_aero(ns)
 
 
 if __name__ == "__main__":

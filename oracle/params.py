@@ -25,6 +25,7 @@ class OrParams(C.Structure):
         ("waypoint", C.c_double), ("landing_radius", C.c_double), ("maximum_velocity", C.c_double),
         ("att_traj_limit", C.c_double * 3), ("att_land_limit", C.c_double * 3), ("omega_lim", C.c_double * 3),
         ("max_gimbal", C.c_double), ("max_thrust", C.c_float), ("obs_mode", C.c_int), ("min_thrust", C.c_float),
+        ("aero_mode", C.c_int),
     ]
 
 
@@ -88,10 +89,13 @@ _DEF_LP = {"waypoint": 50, "landing_radius": 30, "maximum_velocity": 10,
 
 
 def make_params(dof, IC=None, ICRange=None, timestep=0.1, seed=42, reward_coeff=None, trajectory_limits=None,
-                landing_params=None, max_episode_steps=0, reward_mode=0, obs_mode=0, min_thrust=0.0):
+                landing_params=None, max_episode_steps=0, reward_mode=0, obs_mode=0, min_thrust=0.0, aero_mode=0):
     p = OrParams()
     p.obs_mode = int(obs_mode)
     p.min_thrust = float(min_thrust)
+    p.aero_mode = int(aero_mode)
+    if aero_mode and dof == 6:
+        raise ValueError("the angle-of-attack hook is defined for the 3DOF / 1DOF environment (the 6DOF aerodynamic force is a zero stub)")
     if obs_mode and dof != 3:
         raise ValueError("the Gaudet observation is defined for the 3DOF environment")
     p.dof = dof

@@ -57,6 +57,11 @@ typedef struct {
     int    obs_mode;            /* 0 normalised state; 1 (3DOF) GaudetStateObs, corrected (wrappers.py:51-66): see gaudet_obs3 */
     float  min_thrust;          /* EXTENSION (no reference behaviour: the TODO at rocket_env.py:405, :980): lower bound of the
                                    de-normalised thrust; 0 = off */
+    int    aero_mode;           /* EXTENSION, 3DOF / 1DOF: 0 = the reference's behaviour (alfa = 0, simulator.py:103); 1 = the line the
+                                   reference keeps commented out (simulator.py:104, `alfa = self._computeAoA(...)`) enabled, with
+                                   its two defects fixed: the state is passed (not the height), and the missing `_normalize` is
+                                   the wrap to (-pi, pi].  Everything downstream is the reference's own RHS (Cn, N, the N terms of
+                                   ax, ay, dom; simulator.py:107-127).  See rhs3. */
 } OrParams;
 
 /* ------------------------------------------------------------ small helpers */
@@ -129,6 +134,7 @@ typedef struct {
     /* 3DOF per-step constants */
     float  delta3, T3;
     double torque3;     /* (double)( f32(T*sinf(delta)) * 30f ) */
+    int    aero;        /* OrParams.aero_mode */
 } RhsCtx;
 
 static const double J6[3]    = {75350.25, 6037675.13, 6037675.13};
@@ -173,6 +179,17 @@ static void rhs3(const RhsCtx* c, const double* y, double* d) {
     double Q = 0.5 * 1.225 * v2;
     double A = 0.3 * Q * 10.5;
     double N = 0.0;
+    if (c->aero) {
+        /* _computeAoA (simulator.py:132-148) on the state: alfa = phi - arctan2(vz, vx) unless the velocity is exactly zero, then
+         * `_normalize` := _wrapTo2Pi (simulator.py:150-163) folded to (-pi, pi]; Cn = Cnalfa * alfa with Cnalfa = 1, N = Cn * Q * Sref */
+        const double pi = 3.141592653589793, pi2 = 2.0 * 3.141592653589793;
+        double alfa = 0.0;
+        if (!(vx == 0.0 && vz == 0.0)) alfa = phi - atan2(vz, vx);
+        alfa = fmod(fmod(alfa, pi2) + pi2, pi2);
+        if (alfa > pi) alfa = alfa - pi2;
+        double Cn = 1 * alfa;
+        N = Cn * Q * 10.5;
+    }
     double dphi = (double)c->delta3 + phi;
     double ax = (T * cos(dphi) - N * sin(phi) - A * cos(phi)) / mass;
     double ay = (T * sin(dphi) + N * cos(phi) - A * cos(phi)) / mass - 9.81;
@@ -409,6 +426,7 @@ static void denorm_action3_row(const OrParams* p, const float* row, float* u) {
 static double t_of_k(const OrParams* p, int k) { return (double)((int64_t)k * p->dt_ms) / 1000.0; }
 
 static void consts6(RhsCtx* c, const float* u) {
+    c->aero = 0;
     float cy = np_cosf(u[0]), sy = np_sinf(u[0]), cz = np_cosf(u[1]), sz = np_sinf(u[1]);
     float cycz = cy * cz, sycz = sy * cz;
     double T = (double)u[2];
@@ -422,7 +440,7 @@ static void consts6(RhsCtx* c, const float* u) {
     c->dm = (double)((-u[2]) / 3531.6f);
 }
 static void consts3(RhsCtx* c, const float* u) {
-    c->n = 7; c->event_idx = 1;
+    c->n = 7; c->event_idx = 1; c->aero = 0;
     c->delta3 = u[0]; c->T3 = u[1];
     float ts = u[1] * np_sinf(u[0]);
     ts = ts * 30.0f;
@@ -441,6 +459,7 @@ static int sim6_step(const OrParams* p, double* y, int k, const float* u, int* n
 }
 static int sim3_step(const OrParams* p, double* y, int k, const float* u, int* nfev, int* natt) {
     RhsCtx c; consts3(&c, u);
+    c.aero = p->aero_mode;
     double t = t_of_k(p, k);
     int st = rk45_solve(&c, t, t + p->dt, y, nfev, natt);
     const double pi2 = 2.0 * 3.141592653589793;

@@ -11,7 +11,7 @@ MAX_DISCRETE = 16
 NSTATS = 8
 STAT_NAMES = ("steps", "attempts", "done", "landed", "viol", "trunc", "len_sum", "ret_sum_fx")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 FIN_HEADER = 5
 ACT_NORMALIZED, ACT_PHYSICAL, ACT_DISCRETE = 0, 1, 2
 MATH_EXACT, MATH_FAST = 0, 1
@@ -37,6 +37,7 @@ class RlrParams(C.Structure):
         ("max_gimbal", C.c_double), ("max_thrust", C.c_float),
         ("n_discrete", C.c_int32), ("discrete_table", C.c_float * (2 * MAX_DISCRETE)),
         ("discrete_thr", C.c_float * MAX_DISCRETE), ("obs_mode", C.c_int32), ("min_thrust", C.c_float),
+        ("aero_mode", C.c_int32),
     ]
 
 

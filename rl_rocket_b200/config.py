@@ -59,7 +59,8 @@ class EnvSpec:
     """Everything derived from the constructor kwargs: the kernel POD plus the host-side arrays."""
 
     def __init__(self, dof, IC=None, ICRange=None, timestep=None, seed=None, reward_coeff=None, trajectory_limits=None,
-                 landing_params=None, max_episode_steps=0, reward_mode=0, discrete_table=None, obs_mode=0, min_thrust=0.0):
+                 landing_params=None, max_episode_steps=0, reward_mode=0, discrete_table=None, obs_mode=0, min_thrust=0.0,
+                 aero_mode=0):
         if dof not in (6, 3, 1):
             raise ValueError("dof must be 6, 3 or 1")
         d = DEFAULTS_6DOF if dof == 6 else DEFAULTS_3DOF
@@ -80,6 +81,11 @@ class EnvSpec:
             raise ValueError("min_thrust must lie in [0, max_thrust]")
         if self.obs_mode == 1 and dof != 3:
             raise ValueError("obs_mode='gaudet' (GaudetStateObs, wrappers.py:51-66) is defined for the 3DOF environment")
+        # extension: the angle-of-attack line of Simulator3DOF.RHS the reference keeps commented out (simulator.py:103-104)
+        self.aero_mode = {0: 0, 1: 1, False: 0, True: 1, "off": 0, "aoa": 1}[aero_mode]
+        if self.aero_mode and dof == 6:
+            raise ValueError("aero_mode is defined for the 3DOF / 1DOF environment (the reference's 6DOF aerodynamic force is a zero stub, "
+                             "simulator.py:359-360)")
         self.ndim = 14 if dof == 6 else 7
         self.nact = {6: 3, 3: 2, 1: 1}[dof]
         self.nobs = 2 if dof == 1 else (4 if self.obs_mode == 1 else self.ndim)
@@ -162,6 +168,7 @@ class EnvSpec:
         p.dof, p.reward_mode, p.max_episode_steps = self.dof, self.reward_mode, self.max_episode_steps
         p.obs_mode = self.obs_mode
         p.min_thrust = self.min_thrust
+        p.aero_mode = self.aero_mode
         p.dt = float(self.timestep)
         p.dt_ms = timestep_ms(self.timestep)
         rc = self.reward_coeff
@@ -203,7 +210,7 @@ class EnvSpec:
         kw = dict(dof=self.dof, IC=self.IC, ICRange=self.ICRange, timestep=self.timestep, seed=self.seed,
                   reward_coeff=self.reward_coeff, trajectory_limits=self.trajectory_limits, landing_params=self.landing_params,
                   max_episode_steps=self.max_episode_steps, reward_mode=self.reward_mode,
-                  discrete_table=None, obs_mode=self.obs_mode, min_thrust=self.min_thrust)
+                  discrete_table=None, obs_mode=self.obs_mode, min_thrust=self.min_thrust, aero_mode=self.aero_mode)
         kw.update(changes)
         spec = EnvSpec(**kw)
         if self.discrete_table is not None and "discrete_table" not in changes:

@@ -47,6 +47,8 @@ static int check_params(const RlrParams* p) {
     if (p->n_discrete < 0 || p->n_discrete > RLR_MAX_DISCRETE) return fail(RLR_E_INVALID, "n_discrete out of range");
     if (p->obs_mode != RLR_OBS_STATE && p->obs_mode != RLR_OBS_GAUDET) return fail(RLR_E_INVALID, "bad obs_mode");
     if (!(p->min_thrust >= 0.0f) || p->min_thrust > p->max_thrust) return fail(RLR_E_INVALID, "min_thrust must lie in [0, max_thrust]");
+    if (p->aero_mode != 0 && p->aero_mode != 1) return fail(RLR_E_INVALID, "bad aero_mode");
+    if (p->aero_mode != 0 && p->dof == 6) return fail(RLR_E_UNSUPPORTED, "aero_mode is defined for the 3DOF / 1DOF environment (the 6DOF aerodynamic force of the reference is a zero stub, simulator.py:359-360)");
     if (p->obs_mode == RLR_OBS_GAUDET && p->dof != 3) return fail(RLR_E_UNSUPPORTED, "RLR_OBS_GAUDET is defined for the 3DOF environment (wrappers.py:52)");
     return RLR_OK;
 }

@@ -324,6 +324,7 @@ __constant__ double c_P[7][4] = {
 // 6DOF: y = [r(3), v(3), q0..q3, w(3), m]   (simulator.py:259-378)
 struct Sys6 {
     static constexpr int N = 14, EV = 0, NA = 3, NOBS = 14, MAX_REGS = RLR_REGS6;
+    static constexpr bool AERO = false;
     struct Ctx { double Tb0, Tb1, Tb2, tau1, tau2, dm; };
 
     RLR_DEV static void make_ctx(Ctx& c, const float* u) {
@@ -383,6 +384,7 @@ struct Sys6 {
 // 3DOF: y = [x, z, theta, vx, vz, omega, m]   (simulator.py:88-130)
 struct Sys3 {
     static constexpr int N = 7, EV = 1, NA = 2, NOBS = 7, MAX_REGS = 168;
+    static constexpr bool AERO = false;
     struct Ctx { double delta, T, torque, dm, sd, cd; };
 
     RLR_DEV static void make_ctx(Ctx& c, const float* u) {
@@ -423,6 +425,43 @@ struct Sys3 {
 // Same system under a 128-register cap: 4 blocks x 128 threads per SM instead of 3, i.e. one wave instead of 1.15 for 65 536
 // environments (15.0 vs 16.7 us per step); small batches are latency-bound and prefer the spill-free 168-register build.
 struct Sys3Dense : Sys3 { static constexpr int MAX_REGS = 128; };
+
+// EXTENSION (RlrParams.aero_mode = 1): the same system with the angle-of-attack line the reference keeps
+// commented out enabled (simulator.py:103-104) -- alfa = _computeAoA(state) = phi - arctan2(vz, vx) (0 for a zero velocity;
+// simulator.py:132-148), folded to (-pi, pi] by the `_normalize` the reference forgot to define (here: its own _wrapTo2Pi,
+// simulator.py:150-163, minus 2 pi above pi), Cn = Cnalfa alfa (Cnalfa = 1), N = Cn Q Sref, and then the reference's own
+// ax / ay / dom with their N terms (simulator.py:119-125; x_CG - x_CP = -10).  d(omega)/dt now depends on the state, so this system
+// always runs the generic solver (the closed forms of rk45_solve3 need a constant angular acceleration).
+struct Sys3Aero : Sys3 {
+    static constexpr bool AERO = true;
+    RLR_DEV static void rhs(const Ctx& c, const double (&y)[N], double (&d)[N]) {
+        const double phi = y[2], vx = y[3], vz = y[4], mass = y[6];
+        const double v2 = vx * vx + vz * vz;
+        const double Q = (0.5 * 1.225) * v2;
+        const double A = (0.3 * Q) * 10.5;
+        const double pi = 3.141592653589793, pi2 = 2.0 * 3.141592653589793;
+        double alfa = 0.0;
+        if (!(vx == 0.0 && vz == 0.0)) alfa = phi - atan2(vz, vx);
+        alfa = fmod(fmod(alfa, pi2) + pi2, pi2);
+        if (alfa > pi) alfa = alfa - pi2;
+        const double Nf = ((1 * alfa) * Q) * 10.5;
+        double sdp, cdp, sp, cp;
+#if RLR_EXACT
+        sincos(c.delta + phi, &sdp, &cdp);
+        sincos(phi, &sp, &cp);
+#else
+        sincos_fast(phi, &sp, &cp);
+        sdp = c.sd * cp + c.cd * sp;
+        cdp = c.cd * cp - c.sd * sp;
+#endif
+        const double Acp = A * cp;      // the drag multiplies cos(phi) on both axes -- reference behaviour (simulator.py:122-123)
+        d[0] = vx; d[1] = vz; d[2] = y[5];
+        d[3] = RLR_DIV((c.T * cdp - Nf * sp) - Acp, mass);
+        d[4] = RLR_DIV((c.T * sdp + Nf * cp) - Acp, mass) - 9.81;
+        d[5] = (Nf * (double)(10 - 20) - c.torque) / 6.04e6;
+        d[6] = c.dm;
+    }
+};
 
 
 // ------------------------------------------------------------------ RK45 (scipy semantics)
@@ -1811,7 +1850,14 @@ RLR_DEV void env_step(const RlrParams& p, EnvState<S>& st, const float (&u)[3], 
 #if RLR_EXACT
     else status = rk45_solve<S>(c, t, t + p.dt, st.y, natt);
 #else
-    else status = rk45_solve3(c, t, t + p.dt, st.y, natt);
+    else {
+        if constexpr (S::AERO) {
+            if (st.y[6] == 0.0) { natt = 1; status = -1; }        // zero mass: see rk45_solve6
+            else status = rk45_solve<S>(c, t, t + p.dt, st.y, natt);
+        } else {
+            status = rk45_solve3(c, t, t + p.dt, st.y, natt);
+        }
+    }
 #endif
     float s[S::N];
     if constexpr (S::N == 14) {
@@ -2367,6 +2413,9 @@ int launch_step(const RlrParams* p, RlrState st, const void* actions, int action
         const Geometry g = pick_geometry(step_kernel<Sys6>, count, BS6, SMEM6_BYTES);
         launch_pdl(step_kernel<Sys6>, grid_for(count, g.block), g.block, g.smem, stream, *p, st, actions, action_kind, ic_inject, out, n, begin,
                    end, env_offset, seed, is_host_pointer(out.obs));
+    } else if (p->aero_mode != 0) {
+        launch_pdl(step_kernel<Sys3Aero>, grid_for(count, 128), 128, 0, stream, *p, st, actions, action_kind, ic_inject, out, n, begin, end,
+                   env_offset, seed, false);
     } else {
         if (count > 148 * 3 * 128)
             launch_pdl(step_kernel<Sys3Dense>, grid_for(count, 128), 128, 0, stream, *p, st, actions, action_kind, ic_inject, out, n, begin, end,
@@ -2393,6 +2442,9 @@ int launch_rollout(const RlrParams* p, RlrState st, const void* actions, int act
         const Geometry g = pick_geometry(rollout_kernel<Sys6>, n, BS6, SMEM6_BYTES);
         rollout_kernel<Sys6><<<grid_for(n, g.block), g.block, g.smem, stream>>>(*p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf,
                                                                               trunc_buf, last_obs, stats, n, env_offset, seed);
+    } else if (p->aero_mode != 0) {
+        rollout_kernel<Sys3Aero><<<grid_for(n, 128), 128, 0, stream>>>(*p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf, trunc_buf,
+                                                                       last_obs, stats, n, env_offset, seed);
     } else {
         if (n > 148 * 3 * 128)
             rollout_kernel<Sys3Dense><<<grid_for(n, 128), 128, 0, stream>>>(*p, st, actions, action_kind, T, obs_buf, reward_buf, done_buf,

@@ -187,10 +187,11 @@ class Rocket(_SingleEnv):
     metadata = {"render.modes": ["human", "rgb_array"], "render_fps": 10}
     _dof = 3
 
-    def __init__(self, IC=None, ICRange=None, timestep=None, seed=None, reward_coeff=None, device="cuda:0", math_mode="exact", min_thrust=0.0):
+    def __init__(self, IC=None, ICRange=None, timestep=None, seed=None, reward_coeff=None, device="cuda:0", math_mode="exact", min_thrust=0.0,
+                 aero_mode=0):
         self.state_names = ["x", "z", "theta", "vx", "vz", "omega", "mass"]
         self.action_names = ["gimbal", "thrust"]
-        spec = EnvSpec(self._dof, IC, ICRange, timestep, seed, reward_coeff, min_thrust=min_thrust)
+        spec = EnvSpec(self._dof, IC, ICRange, timestep, seed, reward_coeff, min_thrust=min_thrust, aero_mode=aero_mode)
         self._init_common(spec, device, math_mode)
         self.x_bound_right, self.x_bound_left = spec.x_bound_right, spec.x_bound_left
         self.y_bound_up, self.y_bound_down = spec.y_bound_up, spec.y_bound_down

@@ -18,7 +18,7 @@ def _engine():
 def _spec(name, **over):
     EnvSpec, _ = _engine()
     dof, cfgf, tl, mode, akind = G.TRAJ[name]
-    kw = dict(max_episode_steps=tl, reward_mode=mode, obs_mode=G.OBS_MODE.get(name, 0), **cfgf())
+    kw = dict(max_episode_steps=tl, reward_mode=mode, obs_mode=G.OBS_MODE.get(name, 0), aero_mode=G.AERO_MODE.get(name, 0), **cfgf())
     if akind == "discrete":
         kw["discrete_table"] = G.DISCRETE_TABLE
     kw.update(over)
@@ -374,3 +374,37 @@ def test_cooperative_auto_reset_equals_the_reset_kernel(math_mode):
     C = RocketBatch(EnvSpec(6, max_episode_steps=800, **G.cfg6()), N, seed=7, math_mode=math_mode)
     obs_c = C.reset(ic=ic)
     assert torch.equal(A.y, C.y) and torch.equal(A.v0, C.v0) and torch.equal(obs, obs_c)
+
+
+@pytest.mark.parametrize("math_mode", ["exact", "fast"])
+def test_aero_mode_extension_matches_the_oracle(math_mode):
+    """`aero_mode = 1` (extension, SURVEY.md 8(f) N4: the angle-of-attack line of Simulator3DOF.RHS, simulator.py:103-104, enabled):
+    CUDA (`Sys3Aero`, generic solver in both builds) against the C oracle, 2 048 envs x 300 free-running steps with auto-reset; the
+    golden files of the live reference's RHS are replayed by test_golden_trajectories."""
+    from oracle import c_oracle as O
+    EnvSpec, RocketBatch = _engine()
+    cfg, N, T = G.cfg3_default(), 2048, 300
+    spec = EnvSpec(3, max_episode_steps=2000, aero_mode=1, **cfg)
+    p = O.make_params(3, max_episode_steps=2000, aero_mode=1, **cfg)
+    env = RocketBatch(spec, N, seed=11, math_mode=math_mode, debug_outputs=True)
+    vec = O.VecOracle(p, N, seed=11)
+    assert np.abs(env.reset().cpu().numpy().astype(float) - vec.reset(None)).max() <= G.OBS_TOL
+    rng = np.random.RandomState(5)
+    worst, finished = 0.0, 0
+    for t in range(T):
+        a = rng.uniform(-1, 1, (N, 2)).astype(np.float32)
+        env.step_tensor(torch.as_tensor(a).cuda())
+        out = vec.step(a)
+        worst = max(worst, _compare_with_oracle(f"aero 3dof step {t}", spec, env, out))
+        finished += int(out["done"].sum())
+    assert finished > N // 2          # touchdowns / bound violations happened: events and resets are covered
+    print(f"aero_mode [{math_mode}] worst normalised state deviation {worst:.3e}, {finished} finished episodes")
+    # the fused rollout takes the same path
+    env2 = RocketBatch(spec, 512, seed=3, math_mode=math_mode); env3 = RocketBatch(spec, 512, seed=3, math_mode=math_mode)
+    env2.reset(); env3.reset()
+    acts = torch.rand((20, 512, 2), device="cuda") * 2 - 1
+    env2.rollout(acts)
+    for t in range(20):
+        env3.step_tensor(acts[t])
+    dev = ((env2.y - env3.y).abs() / torch.as_tensor(spec.state_normalizer, device="cuda")[:, None]).max().item()
+    assert dev <= (0.0 if math_mode == "exact" else 1e-9)

@@ -89,7 +89,8 @@ def test_kat4_vtarg_grid():
 def test_trajectories_with_autoreset(name):
     dof, cfgf, tl, mode, akind = G.TRAJ[name]
     g = G.load(name)
-    p = O.make_params(dof, max_episode_steps=tl, reward_mode=mode, obs_mode=G.OBS_MODE.get(name, 0), **cfgf())
+    p = O.make_params(dof, max_episode_steps=tl, reward_mode=mode, obs_mode=G.OBS_MODE.get(name, 0),
+                      aero_mode=G.AERO_MODE.get(name, 0), **cfgf())
     norm = np.array(p.normalizer[:O.ndim(p)])
     T, N = g["done"].shape
     vec = O.VecOracle(p, N, seed=int(g["seed"]))
@@ -170,3 +171,33 @@ def test_min_thrust_extension_is_off_by_default_and_floors_the_thrust():
     with pytest.raises(ValueError):
         from rl_rocket_b200.config import EnvSpec
         EnvSpec(6, min_thrust=2e6, **G.cfg6())
+
+
+def test_aero_mode_extension_is_off_by_default_and_vanishes_at_zero_angle_of_attack():
+    """EXTENSION: `aero_mode = 1` enables the angle-of-attack line Simulator3DOF.RHS keeps commented out
+    (simulator.py:103-104); the two golden files traj_3dof*_aero.npz (the live reference's own RHS source with that line enabled,
+    oracle/make_golden.py::aero_fixed) pin it above.  Here: off (0) it changes nothing; on, an incidence of 0.2 rad changes the
+    trajectory while a rocket that starts the step flying along its own axis (alfa = 0 -> N = 0) barely notices; the hook is rejected for the 6DOF environment, whose aerodynamic force is a zero stub."""
+    cfg = G.cfg3_default()
+    ic = np.float32(cfg["IC"])                       # phi = pi/2 (f32), vx = -10, vz = -50
+    off = O.ScalarEnv(O.make_params(3, **cfg)); off.reset(ic)
+    on = O.ScalarEnv(O.make_params(3, aero_mode=1, **cfg)); on.reset(ic)
+    a = np.float32([0.0, -1.0])                      # engine off
+    off.step(a); on.step(a)
+    dev_incidence = np.abs(np.array(off.y) - np.array(on.y)).max()
+    assert dev_incidence > 1e-3                      # incidence: phi - atan2(-50, -10) = 0.2 rad -> a normal force of ~1e5 N
+    # velocity along the body axis (alfa = 0 at the start of the step; gravity turns the velocity by ~0.02 rad during it)
+    phi = float(np.float32(1.2))
+    ic0 = np.float32([0.0, 500.0, phi, 0.0, 0.0, 0.0, 50e3])
+    ic0[3], ic0[4] = np.float32(40.0 * np.cos(phi)), np.float32(40.0 * np.sin(phi))
+    off = O.ScalarEnv(O.make_params(3, **cfg)); off.reset(ic0)
+    on = O.ScalarEnv(O.make_params(3, aero_mode=1, **cfg)); on.reset(ic0)
+    assert np.array_equal(np.array(off.y), np.array(on.y))
+    off.step(a); on.step(a)
+    assert np.abs(np.array(off.y) - np.array(on.y)).max() < 0.05 * dev_incidence
+    with pytest.raises(ValueError):
+        O.make_params(6, aero_mode=1, **G.cfg6())
+    from rl_rocket_b200.config import EnvSpec
+    assert EnvSpec(3, **cfg).params.aero_mode == 0 and EnvSpec(3, aero_mode=1, **cfg).params.aero_mode == 1
+    with pytest.raises(ValueError):
+        EnvSpec(6, aero_mode=1, **G.cfg6())
