@@ -496,21 +496,13 @@ __global__ void __launch_bounds__(BSF) step_kernel_f32(const __grid_constant__ R
             if (out.fin_records) append_fin_record<14>(p, out, n, i, st.ep_ret, st.k, fl, obs);
         }
     }
-    float ic[14];
+    // the finished lanes' reset (initial condition, new state, new observation) is computed and stored by the whole warp
+    // (store_obs_and_reset6_warp, rocket_kernels.cuh); staging planes: row 0 plane a, row 0 plane b, row 1 plane a, row 1 plane b
     const bool finished = active && fl.done;
-    if (ic_inject == nullptr) sample_ic_warp<14>(p, seed, env_offset + i, st.episode + 1, finished, ic);
-    if (active) {
-        if (finished) {
-            st.episode += 1;
-            if (ic_inject != nullptr) {
-#pragma unroll
-                for (int c = 0; c < 14; ++c) ic[c] = ic_inject[i * 14 + c];
-            }
-            reset_from_ic_f(p, ic, st, obs);
-        }
-        store_state_f(gs, n, i, st);
-    }
-    write_obs6_warp_f(p, out.obs, i, active, obs, sKf, stage_obs);
+    if (active && !finished) store_state_f(gs, n, i, st);
+    float* const sKw = sKf + (threadIdx.x >> 5) * 128;
+    store_obs_and_reset6_warp<float>(p, gs, out.obs, n, i, active, finished, st.episode + 1, obs,
+                                     [sKw](int k) { return sKw + (k >> 1) * ROWF + (k & 1) * 4 * BSF; }, stage_obs, ic_inject, seed, env_offset + i);
     accumulate_stats(out.stats, active, fl, ep_len, ep_ret);
 }
 

@@ -1978,19 +1978,21 @@ RLR_DEV void write_obs6_warp(const RlrParams& p, float* dst, int64_t i, bool act
 // nothing.  Same counters, bits and arithmetic as sample_ic / reset_from_ic (the reset kernel and the oracle).  The fused rollout
 // keeps its state in registers across steps and stays with sample_ic_warp + finish_and_reset.
 // `stage`: see write_obs6_warp (host destinations: rows leave as coalesced 16-byte stores through the warp's idle stage-matrix columns).
+// YT: element type of the state arrays (double; float for the RLR_F32 kernels).  plane(k), k = 0..3: the warp's k-th 128-float staging
+// plane in its idle stage-matrix columns (f64 kernels: rows are 64 threads x 16 B = 256 floats apart and a warp owns 128 of them).
+template <class YT, class Plane>
 RLR_DEV void store_obs_and_reset6_warp(const RlrParams& p, const RlrState& gs, float* dst, int64_t n, int64_t i, bool active, bool finished,
-                                         int32_t next_episode, const float (&obs)[14], double* sK, bool stage, const float* ic_inject, uint64_t seed,
-                                         int64_t env) {
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+                                         int32_t next_episode, const float (&obs)[14], Plane plane, bool stage, const float* ic_inject,
+                                         uint64_t seed, int64_t env) {
+    const int lane = threadIdx.x & 31;
     float* tile_dst = dst + (i - lane) * 14;                  // row of the warp's first environment
     const bool staged = stage && __all_sync(0xffffffffu, active) && ((reinterpret_cast<uintptr_t>(tile_dst) & 15) == 0);
-    float* tile = reinterpret_cast<float*>(sK) + w * 128;     // rows are 64 threads x 16 B = 256 floats apart; a warp owns 128 of them
     if (staged) {
         __syncwarp();                                         // every lane is done with its stage-matrix columns
 #pragma unroll
         for (int k = 0; k < 7; ++k) {
             const int o4 = lane * 14 + 2 * k;
-            *reinterpret_cast<float2*>(tile + (o4 >> 7) * 256 + (o4 & 127)) = make_float2(obs[2 * k], obs[2 * k + 1]);
+            *reinterpret_cast<float2*>(plane(o4 >> 7) + (o4 & 127)) = make_float2(obs[2 * k], obs[2 * k + 1]);
         }
         __syncwarp();
     }
@@ -2040,9 +2042,9 @@ RLR_DEV void store_obs_and_reset6_warp(const RlrParams& p, const RlrState& gs, f
                 f0 = fdiv(f0, nq);
                 f1 = fdiv(f1, nq);
             }
-            double* y = (double*)gs.y + i_s;
-            y[(int64_t)(2 * sub) * n] = (double)f0;
-            y[(int64_t)(2 * sub + 1) * n] = (double)f1;
+            YT* y = (YT*)gs.y + i_s;
+            y[(int64_t)(2 * sub) * n] = (YT)f0;
+            y[(int64_t)(2 * sub + 1) * n] = (YT)f1;
 #if RLR_EXACT
             const float o0 = (float)((double)f0 / p.normalizer[2 * sub]), o1 = (float)((double)f1 / p.normalizer[2 * sub + 1]);
 #else
@@ -2050,7 +2052,7 @@ RLR_DEV void store_obs_and_reset6_warp(const RlrParams& p, const RlrState& gs, f
 #endif
             if (staged) {
                 const int o4 = src * 14 + 2 * sub;
-                *reinterpret_cast<float2*>(tile + (o4 >> 7) * 256 + (o4 & 127)) = make_float2(o0, o1);
+                *reinterpret_cast<float2*>(plane(o4 >> 7) + (o4 & 127)) = make_float2(o0, o1);
             } else if (pair_ok) {
                 *reinterpret_cast<float2*>(dst + i_s * 14 + 2 * sub) = make_float2(o0, o1);
             } else {
@@ -2070,7 +2072,7 @@ RLR_DEV void store_obs_and_reset6_warp(const RlrParams& p, const RlrState& gs, f
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const int f = k * 32 + lane;
-            if (f < 112) reinterpret_cast<float4*>(tile_dst)[f] = *reinterpret_cast<const float4*>(tile + k * 256 + 4 * lane);
+            if (f < 112) reinterpret_cast<float4*>(tile_dst)[f] = *reinterpret_cast<const float4*>(plane(k) + 4 * lane);
         }
         __syncwarp();
     }
@@ -2202,8 +2204,9 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
         // ---- 6DOF: the finished lanes' reset (initial condition, new state, new observation) is computed and stored by the whole warp
         if (active && !finished) store_state<S>(gs, n, i, st);
         RLR_PHASE(6);                   // 6: state stores of the continuing environments
-        store_obs_and_reset6_warp(p, gs, out.obs, n, i, active, finished, st.episode + 1, (const float(&)[14])obs, sK, stage_obs, ic_inject, seed,
-                                  env_offset + i);
+        float* const tile = reinterpret_cast<float*>(sK) + (threadIdx.x >> 5) * 128;
+        store_obs_and_reset6_warp<double>(p, gs, out.obs, n, i, active, finished, st.episode + 1, (const float(&)[14])obs,
+                                          [tile](int k) { return tile + k * 256; }, stage_obs, ic_inject, seed, env_offset + i);
         RLR_PHASE(8);                   // 8: observation stores + cooperative auto-reset
     } else {
         // ---- auto-reset: the finished lanes' initial conditions are sampled by the whole warp (sample_ic_warp)
