@@ -461,6 +461,19 @@ __global__ void __launch_bounds__(BSF) step_kernel_f32(const __grid_constant__ R
     EnvStateF st;
     st.episode = 0;
     float obs[14];
+#if RLR_PREFETCH
+    {   // one line per thread, one instruction, before the wait (see prefetch_block_inputs6): 14 x 512 B of state, 1 KB of returns, 1.5 KB of actions
+        const int64_t i0 = i_begin + (int64_t)blockIdx.x * BSF;
+        const int t = threadIdx.x;
+        if (i0 + BSF <= i_end && t < 76) {
+            const char* ptr;
+            if (t < 56) ptr = (const char*)((const float*)gs.y + (int64_t)(t >> 2) * n + i0) + (t & 3) * 128;
+            else if (t < 64) ptr = (const char*)(gs.ep_ret + i0) + (t - 56) * 128;
+            else ptr = (const char*)(actions + i0 * 3) + (t - 64) * 128;
+            prefetch_l2(ptr);
+        }
+    }
+#endif
     pdl_wait_for_predecessor();
     if (active) {
         load_state_f(gs, n, i, st);
