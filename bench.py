@@ -29,7 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ENVS_PER_GPU = 65536
-LEAD_IN = 4                 # untimed steps queued right before the timed ones (after the barrier + synchronize)
+LEAD_IN = int(os.environ.get("RLR_BENCH_LEAD_IN", "4"))      # untimed steps queued right before the timed ones (after the barrier + synchronize)
 PREP_STEPS = 150            # untimed state preparation: desynchronise episodes so resets/events occur at their steady rate
 FLOP_STEP, FLOP_ATTEMPT = 540, 1530      # algorithmic fp64 flop per 6DOF env step: 540 + 1530*k
 BYTES_STEP = 320                          # algorithmic HBM bytes per env step when state round-trips
