@@ -4,8 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W]            # ours (CUDA path through the C ABI)
     python bench.py --impl reference [--steps K] [--warmup W]      # the reference's Python/scipy CPU path (oracle port)
 
-A "step" is one pass of the hot path over one batch: ONE rlr_step launch advancing every environment of the rank by
-one agent step (action mapping -> adaptive RK45 solve with ground event -> reward -> TimeLimit -> auto-reset).
+A "step" is one pass of the hot path over one batch: ONE launch (rlr_step_chained; rlr_step with --serialized) advancing every
+environment of the rank by one agent step (action mapping -> adaptive RK45 solve with ground event -> reward -> TimeLimit -> auto-reset).
 N = 1 runs BASELINE config 3 (6DOF `env_config`, 65 536 envs); N > 1 keeps 65 536 envs per GPU (weak scaling; envs are
 keyed by their global index, no data-path collective) and adds the per-rollout all-gather of the episode statistics
 to the timed region.  Prints ONE JSON line on rank 0.
@@ -16,6 +16,13 @@ set is >= 2 x the L2 capacity ("inputs larger than L2"; the ring size is in `con
 launch with its own event pair behind an L2-flush kernel; an event pair around an EMPTY kernel reads 5 - 6 us on this platform
 (scripts/launch_overhead.cu), so that figure charged ~15 % of timestamping overhead to the kernel -- it is still reported, as
 `variants.single_launch_event_pair_l2_flushed`.
+
+Launch ordering: the workload is a synthetic random-action rollout -- every action exists before the rollout starts -- so the steps are
+enqueued as an open-loop chain (rlr_step_chained): block b of a launch waits for block b of the previous launch on the same batch (the
+only dependency a step has on its predecessor) instead of for the predecessor's whole grid, and the last third of a launch, when only
+the warps with a third RK45 attempt / a ground event / resets are still running, overlaps the body of the next launch.  Same results
+bit for bit (tests/test_gpu_parity.py::test_chained_steps_equal_plain_steps).  `variants.serialized_launches_ring` is the same ring with
+plain rlr_step launches (grid-wide ordering: what a policy network between two steps forces); `--serialized` makes that the headline.
 """
 import argparse
 import json
@@ -128,6 +135,11 @@ def run_ours(args):
 
     n = args.envs_per_gpu
     K, W = args.steps, args.warmup
+    # The actions of a synthetic random-action / fixed-policy rollout exist before the rollout starts, so consecutive steps are enqueued as
+    # an open-loop chain (rlr_step_chained: launch t+1 is ordered after launch t block by block, not grid by grid; results identical to
+    # rlr_step, tests/test_gpu_parity.py::test_chained_steps_equal_plain_steps).  --serialized times plain rlr_step launches instead (what
+    # a policy network between two steps forces); that figure is always reported as variants.serialized_launches_ring.
+    CHAINED = not args.serialized
     cfg = env_config()
     spec = EnvSpec(6, max_episode_steps=800, **cfg)
     # ring of independent batches: combined working set >= 2 x L2, so a launch never finds its state / outputs in L2 (--ring 1: one batch)
@@ -167,7 +179,7 @@ def run_ours(args):
         for b in ring:
             b.step_tensor(chunk[t])
     for t in range(max(W, R)):
-        ring[t % R].step_tensor(actions[t % W])
+        ring[t % R].step_tensor(actions[t % W], chained=CHAINED)
     if world > 1:        # warm-up of the exchange too (first launch: module load; the NCCL fallback sets up its channels: milliseconds)
         for _ in range(3):
             exchange.all_gather(env.stats)
@@ -181,11 +193,11 @@ def run_ours(args):
         exchange.all_gather(env.stats)
     t_wall0 = time.perf_counter()
     for t in range(LEAD_IN):              # untimed lead-in on the same stream: the timed region starts on a busy GPU, as every step of a
-        ring[(t - LEAD_IN) % R].step_tensor(actions[t % W])      # rollout but the first does (ev0's timestamp = the last lead-in step's end)
+        ring[(t - LEAD_IN) % R].step_tensor(actions[t % W], chained=CHAINED)    # rollout but the first does (ev0's timestamp = the last lead-in step's end)
     launches0 = sum(b.launches for b in ring)
     ev0.record()
     for t in range(K):
-        ring[t % R].step_tensor(actions[W + t])
+        ring[t % R].step_tensor(actions[W + t], chained=CHAINED)
     ev_mid.record()
     # per-rollout exchange of returns / done counts (all-gather of the 8-slot statistics record), inside the timed region; the skew the
     # ranks accumulate over their K steps is booked to it (it waits for the slowest rank)
@@ -328,13 +340,22 @@ def run_ours(args):
         single_flushed = n * Kf / (sum(a_.elapsed_time(b_) for a_, b_ in evs) * 1e-3)
         # ---- back-to-back on ONE batch (state L2-resident) and fused-rollout variants, device-timed, for the record
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def bracket(step_fn, steps):
+            for t in range(LEAD_IN):
+                step_fn(t)
+            e0.record()
+            for t in range(steps):
+                step_fn(t)
+            e1.record()
+            e1.synchronize()
+            return n * steps / (e0.elapsed_time(e1) * 1e-3)
+
         torch.cuda.synchronize(dev)
-        e0.record()
-        for t in range(K):
-            env.step_tensor(actions[W + t])
-        e1.record()
-        e1.synchronize()
-        b2b = n * K / (e0.elapsed_time(e1) * 1e-3)
+        b2b = bracket(lambda t: env.step_tensor(actions[W + t % K]), K)
+        b2b_chained = bracket(lambda t: env.step_tensor(actions[W + t % K], chained=True), K)
+        ring_serialized = bracket(lambda t: ring[t % R].step_tensor(actions[W + t % K]), K)
+        ring_chained = bracket(lambda t: ring[t % R].step_tensor(actions[W + t % K], chained=True), K)
         # two independent groups of environments stepped alternately on two streams: the tail of one launch overlaps the body of the next
         # (what the single-stream figures cannot do: griddepcontrol.wait orders consecutive launches of a stream)
         s2 = [torch.cuda.Stream(dev), torch.cuda.Stream(dev)]
@@ -406,7 +427,7 @@ def run_ours(args):
             torch.cuda.synchronize(dev)
             e0.record()
             for t in range(Kv):
-                ringp[t % R].step_tensor(a_fix)
+                ringp[t % R].step_tensor(a_fix, chained=CHAINED)
             e1.record()
             e1.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / Kv
@@ -490,7 +511,9 @@ def run_ours(args):
                 "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": "BASELINE config 3: 6DOF env_config (configuration_file.py:4-34), %d envs per GPU, random U(-1,1) "
-                           "f32 actions, TimeLimit 800, auto-reset, one rlr_step launch per step" % n, "envs_per_gpu": n,
+                           "f32 actions, TimeLimit 800, auto-reset, one %s launch per step" % (n, "rlr_step_chained (open-loop chain: consecutive "
+                           "launches ordered block by block, so a launch's tail overlaps the next launch's body; results identical to rlr_step)"
+                           if CHAINED else "rlr_step"), "envs_per_gpu": n, "launch_ordering": "chained" if CHAINED else "serialized",
                            "total_envs": n * world, "math_mode": args.math,
                            "l2": ("inputs larger than L2: the K timed steps rotate over a ring of %d independent %d-env batches (%.0f MB of state + outputs "
                                   "touched per pass over the ring vs %.0f MB of L2), back to back inside ONE event bracket" % (R, n, R * BYTES_STEP * n / 1e6, l2_bytes / 1e6))
@@ -503,7 +526,8 @@ def run_ours(args):
                                           if world > 1 else None)},
                 "clocks": clocks, "e2e": e2e_d, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
                 "episodes_finished": st_all["done"], "wall_ms_timed_region": wall_ms,
-                "variants": {"single_launch_event_pair_l2_flushed": single_flushed, "back_to_back_one_batch_l2_warm": b2b, "ring_on_two_streams_alternating": two_streams, "fused_rollout_kernel": fused, "f32_state_back_to_back": f32_b2b,
+                "variants": {"single_launch_event_pair_l2_flushed": single_flushed, "serialized_launches_ring": ring_serialized, "chained_launches_ring": ring_chained,
+                             "back_to_back_one_batch_l2_warm": b2b, "back_to_back_one_batch_chained": b2b_chained, "ring_on_two_streams_alternating": two_streams, "fused_rollout_kernel": fused, "f32_state_back_to_back": f32_b2b,
                              "f32_state_fused_rollout": f32_fused, "unit": "env-steps/s (rank 0 only)",
                              "config4_2p20_envs_sharded_all_ranks": config4, **extra},
                 "gather_ms": gather_ms, "steps_ms_sum": sum(step_ms), "per_rank": per_rank}
@@ -535,6 +559,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--math", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--serialized", action="store_true", help="time plain rlr_step launches (grid-wide ordering) instead of the open-loop chain")
     ap.add_argument("--ring", type=int, default=0, help="independent batches the timed steps rotate over (0: enough for 2 x L2; 1: one batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define RLR_ABI_VERSION 5
+#define RLR_ABI_VERSION 6
 #define RLR_NMAX 14          /* state components: 14 (6DOF), 7 (3DOF / 1DOF) */
 #define RLR_MAX_DISCRETE 16
 
@@ -174,6 +174,21 @@ int rlr_step(const RlrParams* p, int precision, int math_mode, RlrState st, cons
 int rlr_step_range(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind,
                    const float* ic_inject, RlrStepOut out, int64_t n, int64_t begin, int64_t count, int64_t env_offset,
                    uint64_t seed, void* stream);
+
+/* Open-loop chaining of consecutive steps (6DOF, RLR_F64): rlr_step, except that block b of the launch orders itself after block b
+ * of the PREVIOUS chained launch on the same state only -- not after everything enqueued before it -- so the tail of one step (the
+ * last third of a launch, when a few warps with a third RK45 attempt / a ground event / resets are still running) overlaps the
+ * body of the next.  For action sources that do not depend on the previous step's results: random / scripted / repeated actions,
+ * the reference's own rollouts (test_6DOF_environment.py:19-27 steps fixed actions), several environment groups stepped in turn.
+ *   block_seq   device u32 [ceil(n / 64)], zero-initialised once, owned by the caller together with the state; one entry per block
+ *   seq_wait    0: this launch waits for everything enqueued before it (start of a chain, or after ANY other operation touched the
+ *               state or the step's outputs); otherwise the seq_publish of the previous chained launch on this state
+ *   seq_publish non-zero, different from seq_wait: stored to block_seq[b] (release) once block b's results are in memory
+ * The caller guarantees that `actions` / `ic_inject` are not produced by work still pending on the stream, and that nothing else on
+ * the stream touches the state or `out` between two launches of one chain.  Results are identical to rlr_step's. */
+int rlr_step_chained(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind,
+                     const float* ic_inject, RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed,
+                     uint32_t* block_seq, uint32_t seq_wait, uint32_t seq_publish, void* stream);
 
 /* T fused steps.  actions: [T][n][nact] (or i64 [T][n] for discrete).  Outputs, when non-NULL, are
  * [T][n][...] rollout buffers (obs/reward/done/truncated) -- the layout SB3's RolloutBuffer uses. */

@@ -11,7 +11,7 @@ MAX_DISCRETE = 16
 NSTATS = 8
 STAT_NAMES = ("steps", "attempts", "done", "landed", "viol", "trunc", "len_sum", "ret_sum_fx")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 FIN_HEADER = 5
 ACT_NORMALIZED, ACT_PHYSICAL, ACT_DISCRETE = 0, 1, 2
 MATH_EXACT, MATH_FAST = 0, 1
@@ -51,7 +51,7 @@ class RlrStepOut(C.Structure):
 
 
 EXPORTS = ("rlr_abi_version", "rlr_last_error", "rlr_sizeof_params", "rlr_ndim", "rlr_nact", "rlr_nobs",
-           "rlr_reset", "rlr_step", "rlr_step_range", "rlr_rollout", "rlr_fma_peak",
+           "rlr_reset", "rlr_step", "rlr_step_range", "rlr_step_chained", "rlr_rollout", "rlr_fma_peak",
            "rlr_pipe_create", "rlr_pipe_destroy", "rlr_pipe_submit", "rlr_pipe_wait",
            "rlr_exchange_create", "rlr_exchange_handle", "rlr_exchange_connect", "rlr_exchange_allgather", "rlr_exchange_status",
            "rlr_exchange_destroy")
@@ -83,6 +83,8 @@ def load():
                              C.c_uint64, C.c_void_p]
     lib.rlr_step_range.argtypes = [P, C.c_int, C.c_int, RlrState, C.c_void_p, C.c_int, C.c_void_p, RlrStepOut, C.c_int64, C.c_int64, C.c_int64,
                                    C.c_int64, C.c_uint64, C.c_void_p]
+    lib.rlr_step_chained.argtypes = [P, C.c_int, C.c_int, RlrState, C.c_void_p, C.c_int, C.c_void_p, RlrStepOut, C.c_int64, C.c_int64,
+                                     C.c_uint64, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
     lib.rlr_rollout.argtypes = [P, C.c_int, C.c_int, RlrState, C.c_void_p, C.c_int, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint64, C.c_void_p]
     lib.rlr_pipe_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]

@@ -9,7 +9,7 @@
 #define RLR_DECLARE_LAUNCHERS(NS)                                                                                                          \
     namespace NS {                                                                                                                         \
     int launch_step(const RlrParams*, RlrState, const void*, int, const float*, RlrStepOut, int64_t, int64_t, int64_t, int64_t, uint64_t,   \
-                    cudaStream_t);                                                                                                          \
+                    cudaStream_t, uint32_t*, uint32_t, uint32_t);                                                                           \
     int launch_reset(const RlrParams*, RlrState, const uint8_t*, const float*, float*, int64_t, int64_t, uint64_t, cudaStream_t);         \
     int launch_rollout(const RlrParams*, RlrState, const void*, int, int, float*, float*, uint8_t*, uint8_t*, float*, unsigned long long*, \
                        int64_t, int64_t, uint64_t, cudaStream_t);                                                                          \
@@ -104,9 +104,30 @@ int rlr_step_range(const RlrParams* p, int precision, int math_mode, RlrState st
     if (precision == RLR_F32)
         return cuda_status(rlr_fast::launch_step_f32(p, st, actions, action_kind, ic_inject, out, n, begin, count, env_offset, seed, s));
     if (math_mode == RLR_MATH_EXACT)
-        return cuda_status(rlr_exact::launch_step(p, st, actions, action_kind, ic_inject, out, n, begin, count, env_offset, seed, s));
+        return cuda_status(rlr_exact::launch_step(p, st, actions, action_kind, ic_inject, out, n, begin, count, env_offset, seed, s, nullptr, 0u, 0u));
     if (math_mode == RLR_MATH_FAST)
-        return cuda_status(rlr_fast::launch_step(p, st, actions, action_kind, ic_inject, out, n, begin, count, env_offset, seed, s));
+        return cuda_status(rlr_fast::launch_step(p, st, actions, action_kind, ic_inject, out, n, begin, count, env_offset, seed, s, nullptr, 0u, 0u));
+    return fail(RLR_E_INVALID, "bad math_mode");
+}
+
+int rlr_step_chained(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind, const float* ic_inject,
+                     RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed, uint32_t* block_seq, uint32_t seq_wait, uint32_t seq_publish,
+                     void* stream) {
+    int rc = check_params(p);
+    if (rc) return rc;
+    if (n < 0) return fail(RLR_E_INVALID, "n < 0");
+    if (p->dof != 6 || precision != RLR_F64) return fail(RLR_E_UNSUPPORTED, "rlr_step_chained is implemented for the 6DOF environment with RLR_F64 state");
+    if (!block_seq || seq_publish == 0u || seq_publish == seq_wait) return fail(RLR_E_INVALID, "rlr_step_chained: block_seq, and a non-zero seq_publish different from seq_wait, are required");
+    if (n == 0) return RLR_OK;
+    if ((rc = check_state(st))) return rc;
+    if (!actions || !out.obs || !out.done) return fail(RLR_E_INVALID, "actions, out.obs and out.done are required");
+    if ((out.fin_records == nullptr) != (out.fin_count == nullptr)) return fail(RLR_E_INVALID, "out.fin_count and out.fin_records go together");
+    if (action_kind != RLR_ACT_NORMALIZED && action_kind != RLR_ACT_PHYSICAL) return fail(RLR_E_INVALID, "bad action_kind");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (math_mode == RLR_MATH_EXACT)
+        return cuda_status(rlr_exact::launch_step(p, st, actions, action_kind, ic_inject, out, n, 0, n, env_offset, seed, s, block_seq, seq_wait, seq_publish));
+    if (math_mode == RLR_MATH_FAST)
+        return cuda_status(rlr_fast::launch_step(p, st, actions, action_kind, ic_inject, out, n, 0, n, env_offset, seed, s, block_seq, seq_wait, seq_publish));
     return fail(RLR_E_INVALID, "bad math_mode");
 }
 

@@ -102,6 +102,30 @@ RLR_DEV void trace_mark(int k) {        // the lowest active lane of whichever p
 // replays, random-action loops) overlap the launch latency and block placement of step t+1 with the tail of step t.
 RLR_DEV void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 RLR_DEV void pdl_wait_for_predecessor() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Open-loop chaining (rlr_step_chained): block b of a launch orders itself after block b of the previous chained launch on the same
+// state -- the only launch-to-launch dependency a step has, since block b works on the same environments in every launch -- through a
+// per-block sequence word, instead of waiting for the predecessor's whole grid.  wait = 0: the ordinary grid-wide wait.
+struct StepChain { uint32_t* block_seq; uint32_t wait, publish; };
+RLR_DEV void chain_wait(const StepChain& ch) {
+    if (ch.wait == 0u) { pdl_wait_for_predecessor(); return; }
+    if (threadIdx.x == 0) {
+        const uint32_t* f = ch.block_seq + blockIdx.x;
+        uint32_t v;
+        for (;;) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+            if (v == ch.wait) break;
+            __nanosleep(40);
+        }
+    }
+    __syncthreads();
+}
+RLR_DEV void chain_publish(const StepChain& ch) {
+    if (ch.publish == 0u) return;
+    // The block barrier orders every thread's result stores before thread 0's release store (release is cumulative over what the
+    // releasing thread has synchronised with: PTX memory model, causality order), so the waiting block's acquire load sees them all.
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ch.block_seq + blockIdx.x), "r"(ch.publish) : "memory");
+}
 
 // ------------------------------------------------------------------ numpy float32 helpers
 // numpy's SIMD float32 sin/cos for |x| < pi/4 (5-FMA Horner). Explicit fmaf:
@@ -2165,10 +2189,12 @@ RLR_DEV void finish_and_reset(const RlrParams& p, EnvState<S>& st, const float* 
     st.ep_ret = 0.0;
 }
 
-template <class S>
+// CHAINED: the rlr_step_chained instantiation (per-block ordering between consecutive launches); the plain instantiation carries none
+// of that code (its mere presence -- a block barrier in a not-taken branch -- cost the plain step 0.5 us)
+template <class S, bool CHAINED = false>
 __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrParams p, RlrState gs, const void* actions, int action_kind,
                                                    const float* ic_inject, RlrStepOut out, int64_t n, int64_t i_begin, int64_t i_end,
-                                                   int64_t env_offset, uint64_t seed, bool stage_obs) {
+                                                   int64_t env_offset, uint64_t seed, bool stage_obs, StepChain chain) {
     // environments [i_begin, i_end) of a batch of n (n is the structure-of-arrays stride; rlr_step passes 0, n)
     extern __shared__ double sK[];
     pdl_launch_dependents();
@@ -2186,7 +2212,7 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
         if (i0 + BS6 <= i_end && action_kind != RLR_ACT_DISCRETE) prefetch_block_inputs6(gs, actions, n, i0);
     }
 #endif
-    pdl_wait_for_predecessor();
+    if constexpr (CHAINED) chain_wait(chain); else pdl_wait_for_predecessor();
     RLR_PHASE(-1);
 
     if (active) {
@@ -2249,6 +2275,7 @@ __global__ void RLR_KERNEL_BOUNDS(S) step_kernel(const __grid_constant__ RlrPara
         }
     }
     accumulate_stats(out.stats, active, fl, ep_len, ep_ret);
+    if constexpr (CHAINED) chain_publish(chain);
     RLR_PHASE(7);                       // 7: obs / state stores, statistics
 #if RLR_WARP_TRACE
     {
@@ -2438,22 +2465,31 @@ inline bool is_host_pointer(const void* ptr) {
 }
 
 int launch_step(const RlrParams* p, RlrState st, const void* actions, int action_kind, const float* ic_inject, RlrStepOut out, int64_t n,
-                int64_t begin, int64_t count, int64_t env_offset, uint64_t seed, cudaStream_t stream) {
+                int64_t begin, int64_t count, int64_t env_offset, uint64_t seed, cudaStream_t stream, uint32_t* block_seq, uint32_t seq_wait,
+                uint32_t seq_publish) {
     const int64_t end = begin + count;
+    const StepChain chain = {block_seq, block_seq ? seq_wait : 0u, block_seq ? seq_publish : 0u};
+    const StepChain nochain = {nullptr, 0u, 0u};
     if (p->dof == 6) {
-        const Geometry g = pick_geometry(step_kernel<Sys6>, count, BS6, SMEM6_BYTES);
-        launch_pdl(step_kernel<Sys6>, grid_for(count, g.block), g.block, g.smem, stream, *p, st, actions, action_kind, ic_inject, out, n, begin,
-                   end, env_offset, seed, is_host_pointer(out.obs));
+        if (chain.block_seq != nullptr) {
+            const Geometry g = pick_geometry(step_kernel<Sys6, true>, count, BS6, SMEM6_BYTES);
+            launch_pdl(step_kernel<Sys6, true>, grid_for(count, g.block), g.block, g.smem, stream, *p, st, actions, action_kind, ic_inject, out, n,
+                       begin, end, env_offset, seed, is_host_pointer(out.obs), chain);
+        } else {
+            const Geometry g = pick_geometry(step_kernel<Sys6>, count, BS6, SMEM6_BYTES);
+            launch_pdl(step_kernel<Sys6>, grid_for(count, g.block), g.block, g.smem, stream, *p, st, actions, action_kind, ic_inject, out, n, begin,
+                       end, env_offset, seed, is_host_pointer(out.obs), nochain);
+        }
     } else if (p->aero_mode != 0) {
         launch_pdl(step_kernel<Sys3Aero>, grid_for(count, 128), 128, 0, stream, *p, st, actions, action_kind, ic_inject, out, n, begin, end,
-                   env_offset, seed, false);
+                   env_offset, seed, false, nochain);
     } else {
         if (count > 148 * 3 * 128)
             launch_pdl(step_kernel<Sys3Dense>, grid_for(count, 128), 128, 0, stream, *p, st, actions, action_kind, ic_inject, out, n, begin, end,
-                       env_offset, seed, false);
+                       env_offset, seed, false, nochain);
         else
             launch_pdl(step_kernel<Sys3>, grid_for(count, 128), 128, 0, stream, *p, st, actions, action_kind, ic_inject, out, n, begin, end,
-                       env_offset, seed, false);
+                       env_offset, seed, false, nochain);
     }
     return (int)cudaGetLastError();
 }

@@ -61,6 +61,9 @@ class RocketBatch:
         self.reward_terms = torch.zeros((6, n), dtype=torch.float64, device=dev) if self.debug else None
         self.vtarg = torch.zeros((4, n), dtype=torch.float64, device=dev) if self.debug else None
         self.launches = 0
+        # open-loop chaining (step_tensor(..., chained=True) -> rlr_step_chained): one sequence word per 64-environment block
+        self._block_seq = torch.zeros(max(1, (n + 63) // 64), dtype=torch.int32, device=dev)
+        self._chain_seq = 0          # seq_publish of the last chained launch; 0 = the chain is broken (the next chained step waits for everything)
         self._started = False        # True once reset() has drawn initial conditions: later explicit resets move to the NEXT episode key
         # the buffers above are persistent, so the pointer structs handed to the C ABI are built once
         self._st = N.RlrState(_ptr(self.y), _ptr(self.k), _ptr(self.episode), _ptr(self.v0), _ptr(self.ep_ret))
@@ -132,14 +135,24 @@ class RocketBatch:
                 else:
                     self.episode += (mask != 0).to(torch.int32)
             self._started = True
+            self._chain_seq = 0
             N.check(self.lib.rlr_reset(self._params_ref, self.precision, self._state(), _ptr(mask), _ptr(ic), _ptr(self.obs),
                                        self.n, self.env_offset, self.seed, self._stream()))
             self.launches += 1
         return self.obs
 
-    def step_tensor(self, actions, physical=False, ic_inject=None):
+    def step_tensor(self, actions, physical=False, ic_inject=None, chained=False):
         """One step for all envs.  actions: cuda f32 [n, nact] (or i64 [n] discrete).  Returns (obs, reward, done) device tensors
-        (views of persistent buffers, overwritten by the next call)."""
+        (views of persistent buffers, overwritten by the next call).
+
+        chained=True (6DOF, f64): open-loop chaining -- consecutive chained steps of this batch are ordered block by block instead of
+        launch by launch, so the tail of one step overlaps the body of the next (rlr_step_chained).  Only for action sources that do
+        not depend on the previous step's results (random / scripted / repeated actions, several batches stepped in turn): `actions`
+        must not be produced by work still pending on the stream, and nothing else may touch this batch's state or outputs on the
+        stream between two chained steps.  Any other method of the batch ends the chain; the results are identical either way."""
+        if chained:
+            return self._step_chained(actions, physical)
+        self._chain_seq = 0
         if (actions.dtype is torch.float32 and tuple(actions.shape) == self._act_shape and actions.is_contiguous()
                 and actions.device == self.device and ic_inject is None):
             # hot path: no per-call allocation, one ctypes call (the caller's current device is restored when it was another GPU)
@@ -166,6 +179,28 @@ class RocketBatch:
             self.launches += 1
         return self.obs, self.reward, self.done
 
+    def _step_chained(self, actions, physical):
+        if self.spec.dof != 6 or self.precision != N.F64:
+            raise ValueError("chained stepping is implemented for the 6DOF environment with precision='f64'")
+        if not (actions.dtype is torch.float32 and tuple(actions.shape) == self._act_shape and actions.is_contiguous()
+                and actions.device == self.device):
+            raise ValueError(f"chained stepping needs contiguous float32 actions of shape {self._act_shape} on {self.device}")
+        prev = torch.cuda.current_device()
+        if prev != self._dev_index:
+            torch.cuda.set_device(self._dev_index)
+        wait = self._chain_seq
+        publish = wait + 1 if wait < 0xFFFFFFF0 else 1
+        rc = self.lib.rlr_step_chained(self._params_ref, self.precision, self.math_mode, self._st, actions.data_ptr(),
+                                       N.ACT_PHYSICAL if physical else N.ACT_NORMALIZED, None, self._ot, self.n, self.env_offset, self.seed,
+                                       self._block_seq.data_ptr(), wait, publish, torch.cuda.current_stream(self._dev_index).cuda_stream)
+        if prev != self._dev_index:
+            torch.cuda.set_device(prev)
+        if rc:
+            N.check(rc)
+        self._chain_seq = publish
+        self.launches += 1
+        return self.obs, self.reward, self.done
+
     def step_out_struct(self, obs, reward, done):
         """An RlrStepOut whose obs / reward / done point at caller-owned buffers (e.g. mapped pinned HOST memory: the kernel then
         writes the step's results straight across PCIe, see RocketVecEnv.step_host); every other output stays on the device.
@@ -184,6 +219,7 @@ class RocketBatch:
             stream = torch.cuda.current_stream(self._dev_index).cuda_stream
         if count is None:
             count = self.n - begin
+        self._chain_seq = 0
         rc = self.lib.rlr_step_range(self._params_ref, self.precision, self.math_mode, self._st, actions_ptr, action_kind, None,
                                      out_struct, self.n, begin, count, self.env_offset, self.seed, stream)
         if prev != self._dev_index:
@@ -195,6 +231,7 @@ class RocketBatch:
     def rollout(self, actions, obs_buf=None, reward_buf=None, done_buf=None, trunc_buf=None, physical=False):
         """T fused steps in ONE launch.  actions: cuda f32 [T, n, nact] (or i64 [T, n]); optional [T, n, ...] output buffers."""
         T = actions.shape[0]
+        self._chain_seq = 0
         actions, kind = self._check_actions(actions, leading=(T,))
         if kind is None:
             kind = N.ACT_PHYSICAL if physical else N.ACT_NORMALIZED

@@ -286,6 +286,7 @@ class _HostPipe:
         prev = torch.cuda.current_device()
         if prev != b._dev_index:
             torch.cuda.set_device(b._dev_index)
+        b._chain_seq = 0              # (a step outside the batch's open-loop chain)
         rc = self.lib.rlr_pipe_submit(self.handle, s, b._params_ref, b.precision, b.math_mode, b._st, a.data_ptr(), d_act.data_ptr(),
                                       a.numel() * a.element_size(), self.kind, out, d_pack.data_ptr(), h_pack.data_ptr(), h_pack.numel(),
                                       b.n, b.env_offset, b.seed, torch.cuda.current_stream(b._dev_index).cuda_stream)

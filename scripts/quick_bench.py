@@ -28,7 +28,8 @@ for N in sizes:
         for t in range(150): env.step_tensor(a[t])     # warm-up: desynchronise episodes
         env.read_stats(reset=True)
         it = iter(range(150, T))
-        ms = timeit(lambda: env.step_tensor(a[next(it)]), 150)
+        CH = os.environ.get("QB_CHAINED", "0") == "1"      # open-loop chaining (rlr_step_chained)
+        ms = timeit(lambda: env.step_tensor(a[next(it)], chained=CH), 150)
         st = env.read_stats(reset=True)
         flops = 540 * st["steps"] + 1530 * st["attempts"]
         if os.environ.get("QB_FLUSH", "1") == "1":       # what bench.py times: one launch per event pair, L2 evicted in between
@@ -51,7 +52,7 @@ for N in sizes:
                 for t in range(150): e.step_tensor(a[t])
             cnt = [0]
             def rot():
-                envs[cnt[0] % R].step_tensor(a[150 + cnt[0] % 150]); cnt[0] += 1
+                envs[cnt[0] % R].step_tensor(a[150 + cnt[0] % 150], chained=CH); cnt[0] += 1
             for _ in range(2 * R): rot()
             msr = timeit(rot, 40 * R)
             print(f"[{tag}] {prec} step {mode} N={N} rotating over {R} batches, back to back: {msr*1e3:.1f} us/step", flush=True)

@@ -408,3 +408,47 @@ def test_aero_mode_extension_matches_the_oracle(math_mode):
         env3.step_tensor(acts[t])
     dev = ((env2.y - env3.y).abs() / torch.as_tensor(spec.state_normalizer, device="cuda")[:, None]).max().item()
     assert dev <= (0.0 if math_mode == "exact" else 1e-9)
+
+
+@pytest.mark.parametrize("math_mode", ["exact", "fast"])
+def test_chained_steps_equal_plain_steps(math_mode):
+    """Open-loop chaining (rlr_step_chained: block b of a launch orders itself after block b of the previous chained launch on the
+    same state, not after the whole predecessor grid) changes when blocks run, not what they compute: 300 chained steps of one batch
+    -- with resets, ground events and a chain broken by a plain step, a masked reset and a rollout in the middle -- and a ring of three
+    batches stepped in turn give bit-identical state, outputs and statistics to plain steps."""
+    EnvSpec, RocketBatch = _engine()
+    N, T = 20000, 300                       # 313 blocks, the last one partial
+    spec = EnvSpec(6, max_episode_steps=60, **G.cfg6())
+    g = torch.Generator(device="cuda").manual_seed(9)
+    acts = torch.rand((T, N, 3), device="cuda", generator=g) * 2 - 1
+    A = RocketBatch(spec, N, seed=5, math_mode=math_mode)
+    B = RocketBatch(spec, N, seed=5, math_mode=math_mode)
+    A.reset(); B.reset()
+    for t in range(T):
+        if t == 100:                        # a plain step, a masked reset and a fused rollout break the chain and restart it
+            A.step_tensor(acts[t]); B.step_tensor(acts[t])
+            m = (torch.arange(N, device="cuda") % 7 == 0)
+            A.reset(mask=m); B.reset(mask=m)
+            A.rollout(acts[t:t + 3]); B.rollout(acts[t:t + 3])
+            continue
+        oa, ra, da = A.step_tensor(acts[t], chained=True)
+        ob, rb, db = B.step_tensor(acts[t])
+        if t % 25 == 0 or t == T - 1:
+            assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), f"step {t}"
+            assert torch.equal(A.y, B.y) and torch.equal(A.k, B.k) and torch.equal(A.episode, B.episode) and torch.equal(A.ep_ret, B.ep_ret)
+    assert A.read_stats() == B.read_stats() and A.read_stats()["done"] > N
+    # three batches stepped in turn on one stream (what bench.py's ring does), chained vs plain
+    ring_c = [RocketBatch(spec, 4096, seed=20 + j, math_mode=math_mode) for j in range(3)]
+    ring_p = [RocketBatch(spec, 4096, seed=20 + j, math_mode=math_mode) for j in range(3)]
+    for b in ring_c + ring_p:
+        b.reset()
+    acts4 = acts[:90, :4096].contiguous()           # (the actions of a chained step must exist before the step is enqueued)
+    torch.cuda.synchronize()
+    for t in range(90):
+        ring_c[t % 3].step_tensor(acts4[t], chained=True)
+    for t in range(90):
+        ring_p[t % 3].step_tensor(acts4[t])
+    for c, p_ in zip(ring_c, ring_p):
+        assert torch.equal(c.y, p_.y) and torch.equal(c.obs, p_.obs) and c.read_stats() == p_.read_stats()
+    with pytest.raises(ValueError):
+        RocketBatch(EnvSpec(3, **G.cfg3()), 64).step_tensor(torch.zeros((64, 2), device="cuda"), chained=True)

@@ -29,7 +29,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert set(syms) == set(N.EXPORTS), (syms, N.EXPORTS)
     for s in syms:
         assert hasattr(lib, s), f"{s} declared in the header but not exported"
-    assert lib.rlr_abi_version() == N.ABI_VERSION == 5
+    assert lib.rlr_abi_version() == N.ABI_VERSION == 6
     assert lib.rlr_sizeof_params() == ctypes.sizeof(N.RlrParams)
 
 
