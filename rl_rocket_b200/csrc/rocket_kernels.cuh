@@ -111,7 +111,7 @@ RLR_DEV void chain_wait(const StepChain& ch) {
     if (threadIdx.x == 0) {
         const uint32_t* f = ch.block_seq + blockIdx.x;
         uint32_t v;
-        for (;;) {
+        for (int spins = 0; spins < (1 << 22); ++spins) {         // bounded (~2 s): a broken chain must not hang the GPU
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
             if (v == ch.wait) break;
             __nanosleep(40);
