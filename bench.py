@@ -21,7 +21,8 @@ Launch ordering: the workload is a synthetic random-action rollout -- every acti
 enqueued as an open-loop chain (rlr_step_chained): block b of a launch waits for block b of the previous launch on the same batch (the
 only dependency a step has on its predecessor) instead of for the predecessor's whole grid, and the last third of a launch, when only
 the warps with a third RK45 attempt / a ground event / resets are still running, overlaps the body of the next launch.  Same results
-bit for bit (tests/test_gpu_parity.py::test_chained_steps_equal_plain_steps).  `variants.serialized_launches_ring` is the same ring with
+(tests/test_gpu_parity.py::test_chained_steps_equal_plain_steps: bit for bit in the exact build, flags / counters identical and the state
+within 1e-15 in the fast build, whose chained kernel is a separate compilation).  `variants.serialized_launches_ring` is the same ring with
 plain rlr_step launches (grid-wide ordering: what a policy network between two steps forces); `--serialized` makes that the headline.
 """
 import argparse
@@ -136,7 +137,7 @@ def run_ours(args):
     n = args.envs_per_gpu
     K, W = args.steps, args.warmup
     # The actions of a synthetic random-action / fixed-policy rollout exist before the rollout starts, so consecutive steps are enqueued as
-    # an open-loop chain (rlr_step_chained: launch t+1 is ordered after launch t block by block, not grid by grid; results identical to
+    # an open-loop chain (rlr_step_chained: launch t+1 is ordered after launch t block by block, not grid by grid; same results as
     # rlr_step, tests/test_gpu_parity.py::test_chained_steps_equal_plain_steps).  --serialized times plain rlr_step launches instead (what
     # a policy network between two steps forces); that figure is always reported as variants.serialized_launches_ring.
     CHAINED = not args.serialized
@@ -512,7 +513,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": "BASELINE config 3: 6DOF env_config (configuration_file.py:4-34), %d envs per GPU, random U(-1,1) "
                            "f32 actions, TimeLimit 800, auto-reset, one %s launch per step" % (n, "rlr_step_chained (open-loop chain: consecutive "
-                           "launches ordered block by block, so a launch's tail overlaps the next launch's body; results identical to rlr_step)"
+                           "launches ordered block by block, so a launch's tail overlaps the next launch's body; same results as rlr_step)"
                            if CHAINED else "rlr_step"), "envs_per_gpu": n, "launch_ordering": "chained" if CHAINED else "serialized",
                            "total_envs": n * world, "math_mode": args.math,
                            "l2": ("inputs larger than L2: the K timed steps rotate over a ring of %d independent %d-env batches (%.0f MB of state + outputs "

@@ -185,7 +185,9 @@ int rlr_step_range(const RlrParams* p, int precision, int math_mode, RlrState st
  *               state or the step's outputs); otherwise the seq_publish of the previous chained launch on this state
  *   seq_publish non-zero, different from seq_wait: stored to block_seq[b] (release) once block b's results are in memory
  * The caller guarantees that `actions` / `ic_inject` are not produced by work still pending on the stream, and that nothing else on
- * the stream touches the state or `out` between two launches of one chain.  Results are identical to rlr_step's. */
+ * the stream touches the state or `out` between two launches of one chain.  Results: bit-identical to rlr_step's with RLR_MATH_EXACT;
+ * with RLR_MATH_FAST the chained kernel is a separate compilation (FMA contraction may differ in the last bit: <= 1e-15 normalised),
+ * flags / counters / attempt counts identical. */
 int rlr_step_chained(const RlrParams* p, int precision, int math_mode, RlrState st, const void* actions, int action_kind,
                      const float* ic_inject, RlrStepOut out, int64_t n, int64_t env_offset, uint64_t seed,
                      uint32_t* block_seq, uint32_t seq_wait, uint32_t seq_publish, void* stream);

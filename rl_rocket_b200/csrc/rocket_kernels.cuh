@@ -121,8 +121,9 @@ RLR_DEV void chain_wait(const StepChain& ch) {
 }
 RLR_DEV void chain_publish(const StepChain& ch) {
     if (ch.publish == 0u) return;
-    // The block barrier orders every thread's result stores before thread 0's release store (release is cumulative over what the
-    // releasing thread has synchronised with: PTX memory model, causality order), so the waiting block's acquire load sees them all.
+    // Every thread makes its own result stores visible at device scope, then the block barrier, then one release store for the block.
+    // (The per-thread fence is conservative: the release is cumulative over the barrier in the PTX memory model; it costs 0.3 us.)
+    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(ch.block_seq + blockIdx.x), "r"(ch.publish) : "memory");
 }
@@ -1956,10 +1957,12 @@ RLR_DEV void prefetch_block_inputs6(const RlrState& gs, const void* actions, int
 }
 template <class S>
 RLR_DEV void load_state(const RlrState& gs, int64_t n, int64_t i, EnvState<S>& st) {
+    // ld.global.cg: every element is read once (nothing to gain from L1), and a chained launch (rlr_step_chained) may run on an SM
+    // whose L1 was last invalidated before the predecessor block stored these very lines -- L2 is the point of coherence
     const double* y = (const double*)gs.y + i;
 #pragma unroll
-    for (int c = 0; c < S::N; ++c, y += n) st.y[c] = *y;
-    st.k = gs.k[i]; st.episode = gs.episode[i]; st.v0 = gs.v0[i]; st.ep_ret = gs.ep_ret[i];
+    for (int c = 0; c < S::N; ++c, y += n) st.y[c] = __ldcg(y);
+    st.k = __ldcg(gs.k + i); st.episode = __ldcg(gs.episode + i); st.v0 = __ldcg(gs.v0 + i); st.ep_ret = __ldcg(gs.ep_ret + i);
 }
 template <class S>
 RLR_DEV void store_state(const RlrState& gs, int64_t n, int64_t i, const EnvState<S>& st) {

@@ -415,10 +415,29 @@ def test_chained_steps_equal_plain_steps(math_mode):
     """Open-loop chaining (rlr_step_chained: block b of a launch orders itself after block b of the previous chained launch on the
     same state, not after the whole predecessor grid) changes when blocks run, not what they compute: 300 chained steps of one batch
     -- with resets, ground events and a chain broken by a plain step, a masked reset and a rollout in the middle -- and a ring of three
-    batches stepped in turn give bit-identical state, outputs and statistics to plain steps."""
+    batches stepped in turn against plain steps.  Exact build: bit-identical state, outputs and statistics.  Fast build: the chained
+    and the plain kernel are two compilations of the same source and ptxas contracts multiply-adds per kernel, so the state may differ
+    in the last bits (measured 1e-15 of the normaliser); done / truncated flags, episode counters, step counters and the statistics'
+    counts must still be identical."""
     EnvSpec, RocketBatch = _engine()
     N, T = 20000, 300                       # 313 blocks, the last one partial
     spec = EnvSpec(6, max_episode_steps=60, **G.cfg6())
+    norm = torch.as_tensor(spec.state_normalizer, device="cuda")[:, None]
+    tol = 0.0 if math_mode == "exact" else 1e-12
+
+    def same(a, b, t):
+        assert torch.equal(a.done, b.done) and torch.equal(a.truncated, b.truncated) and torch.equal(a.flags, b.flags), f"step {t}: flags"
+        assert torch.equal(a.k, b.k) and torch.equal(a.episode, b.episode), f"step {t}: counters"
+        assert ((a.y - b.y).abs() / norm).max().item() <= tol, f"step {t}: state"
+        assert (a.obs - b.obs).abs().max().item() <= (0.0 if tol == 0.0 else 2e-7), f"step {t}: obs"
+        assert (a.reward64 - b.reward64).abs().max().item() <= tol * 1e3 and (a.ep_ret - b.ep_ret).abs().max().item() <= tol * 1e5, f"step {t}: reward"
+
+    def same_stats(a, b):
+        sa, sb = a.read_stats(), b.read_stats()
+        assert {k: v for k, v in sa.items() if k != "ret_sum"} == {k: v for k, v in sb.items() if k != "ret_sum"}
+        assert abs(sa["ret_sum"] - sb["ret_sum"]) <= (0.0 if tol == 0.0 else 1e-3)
+        return sa
+
     g = torch.Generator(device="cuda").manual_seed(9)
     acts = torch.rand((T, N, 3), device="cuda", generator=g) * 2 - 1
     A = RocketBatch(spec, N, seed=5, math_mode=math_mode)
@@ -431,17 +450,17 @@ def test_chained_steps_equal_plain_steps(math_mode):
             A.reset(mask=m); B.reset(mask=m)
             A.rollout(acts[t:t + 3]); B.rollout(acts[t:t + 3])
             continue
-        oa, ra, da = A.step_tensor(acts[t], chained=True)
-        ob, rb, db = B.step_tensor(acts[t])
+        A.step_tensor(acts[t], chained=True)
+        B.step_tensor(acts[t])
         if t % 25 == 0 or t == T - 1:
-            assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), f"step {t}"
-            assert torch.equal(A.y, B.y) and torch.equal(A.k, B.k) and torch.equal(A.episode, B.episode) and torch.equal(A.ep_ret, B.ep_ret)
-    assert A.read_stats() == B.read_stats() and A.read_stats()["done"] > N
+            same(A, B, t)
+    assert same_stats(A, B)["done"] > N
     # three batches stepped in turn on one stream (what bench.py's ring does), chained vs plain
     ring_c = [RocketBatch(spec, 4096, seed=20 + j, math_mode=math_mode) for j in range(3)]
     ring_p = [RocketBatch(spec, 4096, seed=20 + j, math_mode=math_mode) for j in range(3)]
     for b in ring_c + ring_p:
         b.reset()
+    norm = norm[:, :1]
     acts4 = acts[:90, :4096].contiguous()           # (the actions of a chained step must exist before the step is enqueued)
     torch.cuda.synchronize()
     for t in range(90):
@@ -449,6 +468,7 @@ def test_chained_steps_equal_plain_steps(math_mode):
     for t in range(90):
         ring_p[t % 3].step_tensor(acts4[t])
     for c, p_ in zip(ring_c, ring_p):
-        assert torch.equal(c.y, p_.y) and torch.equal(c.obs, p_.obs) and c.read_stats() == p_.read_stats()
+        same(c, p_, 90)
+        same_stats(c, p_)
     with pytest.raises(ValueError):
         RocketBatch(EnvSpec(3, **G.cfg3()), 64).step_tensor(torch.zeros((64, 2), device="cuda"), chained=True)
