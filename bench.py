@@ -37,7 +37,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ENVS_PER_GPU = 65536
-LEAD_IN = int(os.environ.get("RLR_BENCH_LEAD_IN", "4"))      # untimed steps queued right before the timed ones (after the barrier + synchronize)
+# untimed steps queued right before the timed ones (after the barrier + synchronize): a chain of overlapping launches needs ~10 steps
+# from an idle GPU until its blocks have drifted apart to their steady state (20 timed steps read 19.7 / 18.9 / 18.7 us with 4 / 16 / 32)
+LEAD_IN = int(os.environ.get("RLR_BENCH_LEAD_IN", "16"))
 PREP_STEPS = 150            # untimed state preparation: desynchronise episodes so resets/events occur at their steady rate
 FLOP_STEP, FLOP_ATTEMPT = 540, 1530      # algorithmic fp64 flop per 6DOF env step: 540 + 1530*k
 BYTES_STEP = 320                          # algorithmic HBM bytes per env step when state round-trips
@@ -178,7 +180,7 @@ def run_ours(args):
     # state preparation and warm-up run AFTER the sampler's start-up pause, so that the GPU is busy (clocks up) right before the timed region
     for t in range(PREP_STEPS):
         for b in ring:
-            b.step_tensor(chunk[t])
+            b.step_tensor(chunk[t], chained=CHAINED)
     for t in range(max(W, R)):
         ring[t % R].step_tensor(actions[t % W], chained=CHAINED)
     if world > 1:        # warm-up of the exchange too (first launch: module load; the NCCL fallback sets up its channels: milliseconds)

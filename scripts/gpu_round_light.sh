@@ -10,6 +10,6 @@ python bench.py --steps 20 --warmup 5 > $O/${TAG}_bench_steps20.json 2>> $O/${TA
 python bench.py --impl reference --steps 3 --warmup 3 > $O/${TAG}_bench_ref.json 2>> $O/${TAG}_bench.err; echo "ref exit $?"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2300 --csv --log-file $O/${TAG}_launches.csv \
     python bench.py --steps 100 --warmup 10 --no-cpu-baseline > $O/${TAG}_ncu_list.log 2>&1; echo "ncu list exit $?"
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:step_kernel<rlr_fast::Sys6, true>" -s 1965 -c 1 -f \
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k "regex:step_kernel<rlr_fast::Sys6, .bool.1>" -s 1965 -c 1 -f \
     -o $O/${TAG}_stepchained python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $O/${TAG}_ncu_stepchained.log 2>&1; echo "ncu chained exit $?"
 ls -la $O | grep ${TAG}
