@@ -190,6 +190,11 @@ def run_ours(args):
     env.read_stats(reset=True)
     ev0, ev_mid, ev1 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     barrier()
+    # The whole sequence -- rendezvous, lead-in, the K timed steps, the exchange -- is enqueued behind a ~2 ms device-side sleep, so the GPU
+    # runs it from a full launch queue: a host hiccup of a few tens of microseconds (one rank of eight descheduled for 50 us was enough)
+    # would otherwise starve the stream inside a region that lasts 0.4 ms at K = 20 and be booked as step or exchange time.
+    if hasattr(torch.cuda, "_sleep"):
+        torch.cuda._sleep(4_000_000)
     if world > 1:
         # device-side rendezvous right before the timed region: the host barrier releases the ranks tens of microseconds apart, and a
         # rank that starts early would otherwise book that skew as time spent waiting in the rollout's exchange
