@@ -14,6 +14,8 @@
  *                  + wrappers DiscreteActions3DOF / RewardAnnealing (my_environment/wrappers/wrappers.py:24-35,68-86)
  *   rlr_step_range the same step restricted to the environments [begin, begin + count) of the batch (sub-batch pipelining:
  *                  several ranges on different streams, so one range's PCIe transfers overlap another's integration)
+ *   rlr_step_chained  rlr_step for open-loop action sources (the reference's own rollouts step fixed / sampled actions,
+ *                  test_6DOF_environment.py:19-27): consecutive launches ordered block by block instead of grid by grid
  *   rlr_rollout    T consecutive rlr_step calls fused in one launch (state stays in registers)
  *   RlrStepOut.stats / fin_ret / fin_len   the per-episode bookkeeping SB3's Monitor does on the host (main.py:65-70),
  *                  accumulated on the device by the step / rollout kernels (there is no separate statistics entry point)

@@ -51,6 +51,25 @@ def test_abi_argument_validation_without_gpu():
     assert lib.rlr_reset(ctypes.byref(spec3d.params), N.F32, N.RlrState(1, 1, 1, 1, 1), None, None, None, 4, 0, 0, None) == -3      # f32 state: 6DOF only
 
 
+def test_step_chained_argument_validation_without_gpu():
+    lib = N.load()
+    spec = EnvSpec(6, **G.cfg6())
+    st, out = N.RlrState(1, 1, 1, 1, 1), N.RlrStepOut()
+    out.obs, out.done = 1, 1
+    P = ctypes.byref(spec.params)
+    # block_seq, and a non-zero seq_publish different from seq_wait, are required
+    assert lib.rlr_step_chained(P, N.F64, N.MATH_FAST, st, 1, N.ACT_NORMALIZED, None, out, 64, 0, 0, None, 0, 1, None) == -1
+    assert lib.rlr_step_chained(P, N.F64, N.MATH_FAST, st, 1, N.ACT_NORMALIZED, None, out, 64, 0, 0, 1, 0, 0, None) == -1
+    assert lib.rlr_step_chained(P, N.F64, N.MATH_FAST, st, 1, N.ACT_NORMALIZED, None, out, 64, 0, 0, 1, 3, 3, None) == -1
+    assert b"seq_publish" in lib.rlr_last_error()
+    # 6DOF, f64 state only; an empty batch is a no-op
+    assert lib.rlr_step_chained(P, N.F32, N.MATH_FAST, st, 1, N.ACT_NORMALIZED, None, out, 64, 0, 0, 1, 0, 1, None) == -3
+    assert lib.rlr_step_chained(ctypes.byref(EnvSpec(3, **G.cfg3()).params), N.F64, N.MATH_FAST, st, 1, N.ACT_NORMALIZED, None, out, 64, 0, 0, 1, 0, 1,
+                                None) == -3
+    assert lib.rlr_step_chained(P, N.F64, N.MATH_FAST, st, 1, N.ACT_NORMALIZED, None, out, 0, 0, 0, 1, 0, 1, None) == 0
+    assert lib.rlr_step_chained(P, N.F64, N.MATH_FAST, N.RlrState(None, None, None, None, None), 1, N.ACT_NORMALIZED, None, out, 64, 0, 0, 1, 0, 1, None) == -1
+
+
 def test_envspec_matches_reference_constants():
     # values the live reference computes for configuration_file.env_config
     s = EnvSpec(6, **G.cfg6())
