@@ -115,6 +115,7 @@ class RocketBatch:
         self.seed = int(seed)
         self.episode.zero_()
         self._started = False
+        self._chain_seq = 0
 
     def reset(self, mask=None, ic=None):
         """(Re)start environments; returns the obs tensor [n, nobs] (device).  `ic`: optional f32 [n, ndim] initial conditions.
