@@ -78,8 +78,12 @@ class RocketVecEnv(_VecEnvBase):
             self.trace.start()
         return obs
 
-    def step_tensor(self, actions):
-        out = self.batch.step_tensor(actions)
+    def step_tensor(self, actions, chained=False):
+        """Tensor-native step (no host synchronisation).  chained=True: open-loop chaining of consecutive steps (6DOF, f64; see
+        RocketBatch.step_tensor) -- for action sources that do not need the previous step's results; not with a trajectory trace."""
+        if chained and self.trace is not None:
+            raise ValueError("chained stepping cannot be combined with a trajectory trace (the trace reads every step's outputs)")
+        out = self.batch.step_tensor(actions, chained=chained)
         if self.trace is not None:
             self.trace.record(actions)
         return out
