@@ -37,9 +37,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 ENVS_PER_GPU = 65536
-# untimed steps queued right before the timed ones (after the barrier + synchronize): a chain of overlapping launches needs ~10 steps
-# from an idle GPU until its blocks have drifted apart to their steady state (20 timed steps read 19.7 / 18.9 / 18.7 us with 4 / 16 / 32)
-LEAD_IN = int(os.environ.get("RLR_BENCH_LEAD_IN", "16"))
+# untimed steps queued right before the timed ones (after the barrier + synchronize): a chain of overlapping launches needs some steps
+# from an idle GPU until its blocks have drifted apart to their steady state (20 timed steps read 19.7 / 18.9 / 18.7 us after 4 / 16 / 32
+# lead-in steps; behind the device-side sleep below: 19.4 after 16, 18.9 - 19.0 after 48)
+LEAD_IN = int(os.environ.get("RLR_BENCH_LEAD_IN", "48"))
+GATE_CYCLES = int(os.environ.get("RLR_BENCH_GATE_CYCLES", "4000000"))     # device-side sleep the timed sequence is enqueued behind (~2 ms)
 PREP_STEPS = 150            # untimed state preparation: desynchronise episodes so resets/events occur at their steady rate
 FLOP_STEP, FLOP_ATTEMPT = 540, 1530      # algorithmic fp64 flop per 6DOF env step: 540 + 1530*k
 BYTES_STEP = 320                          # algorithmic HBM bytes per env step when state round-trips
@@ -193,8 +195,8 @@ def run_ours(args):
     # The whole sequence -- rendezvous, lead-in, the K timed steps, the exchange -- is enqueued behind a ~2 ms device-side sleep, so the GPU
     # runs it from a full launch queue: a host hiccup of a few tens of microseconds (one rank of eight descheduled for 50 us was enough)
     # would otherwise starve the stream inside a region that lasts 0.4 ms at K = 20 and be booked as step or exchange time.
-    if hasattr(torch.cuda, "_sleep"):
-        torch.cuda._sleep(4_000_000)
+    if hasattr(torch.cuda, "_sleep") and GATE_CYCLES > 0:
+        torch.cuda._sleep(GATE_CYCLES)
     if world > 1:
         # device-side rendezvous right before the timed region: the host barrier releases the ranks tens of microseconds apart, and a
         # rank that starts early would otherwise book that skew as time spent waiting in the rollout's exchange
