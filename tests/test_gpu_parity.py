@@ -430,7 +430,9 @@ def test_chained_steps_equal_plain_steps(math_mode):
         assert torch.equal(a.k, b.k) and torch.equal(a.episode, b.episode), f"step {t}: counters"
         assert ((a.y - b.y).abs() / norm).max().item() <= tol, f"step {t}: state"
         assert (a.obs - b.obs).abs().max().item() <= (0.0 if tol == 0.0 else 2e-7), f"step {t}: obs"
-        assert (a.reward64 - b.reward64).abs().max().item() <= tol * 1e3 and (a.ep_ret - b.ep_ret).abs().max().item() <= tol * 1e5, f"step {t}: reward"
+        # (the reward is evaluated on the float32 copy of the state, rocket_env.py:695: a last-bit difference of the f64 state can flip
+        # a float32 rounding, which moves a reward term by ~1e-8 and the running return with it)
+        assert (a.reward64 - b.reward64).abs().max().item() <= tol * 1e6 and (a.ep_ret - b.ep_ret).abs().max().item() <= tol * 1e8, f"step {t}: reward"
 
     def same_stats(a, b):
         sa, sb = a.read_stats(), b.read_stats()
